@@ -1,0 +1,69 @@
+"""Build libdiffute_b200.so in-tree with nvcc for sm_100a (no torch types in the ABI, loaded via ctypes)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdiffute_b200.so")
+STAMP = os.path.join(HERE, "csrc", ".build_stamp")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("DFU_PTXAS_V") else "-O3"]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + ["../../include/diffute_b200.h"]:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p) and (f.endswith((".cu", ".cuh", ".h"))):
+            h.update(f.encode())
+            h.update(open(p, "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    if not os.path.exists(NVCC):
+        if os.path.exists(LIB):
+            return LIB  # GPU box without a changed tree: use the prebuilt library that travelled with the snapshot
+        raise RuntimeError("nvcc not found and no prebuilt libdiffute_b200.so")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    ok = True
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            ok = False
+            sys.stderr.write(f"nvcc failed for {src}:\n{out}\n")
+        elif verbose and out.strip():
+            print(out)
+    if not ok:
+        raise RuntimeError("nvcc compilation failed")
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    with open(STAMP, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,86 @@
+"""ctypes binding of libdiffute_b200.so (the C-ABI declared in include/diffute_b200.h).
+
+The library is the only compute path: if it is missing, or a call fails, we raise — there is no
+CPU / PyTorch fallback anywhere in diffute_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiffute_b200.so")
+
+
+class DfuError(RuntimeError):
+    pass
+
+
+class GemmOperand(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_mode", C.c_int32), ("a_rows", C.c_int32), ("a_ld", C.c_int32),
+        ("a_h", C.c_int32), ("a_w", C.c_int32), ("a_c", C.c_int32), ("a_plane", C.c_int32),
+        ("b", C.c_void_p), ("b_rows", C.c_int32), ("b_ld", C.c_int32), ("b_plane", C.c_int32),
+        ("ntaps", C.c_int32), ("k_per_tap", C.c_int32),
+        ("tap_dn", C.c_int8 * 9), ("tap_dy", C.c_int8 * 9), ("tap_dx", C.c_int8 * 9), ("_pad", C.c_int8 * 5),
+    ]
+
+
+class Gemm(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32), ("n", C.c_int32), ("ngroups", C.c_int32), ("npass", C.c_int32),
+        ("g", GemmOperand * 2),
+        ("conv", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("epi", C.c_int32), ("alpha", C.c_float),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int32), ("rows_per_sample", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int32),
+        ("out_f32", C.c_void_p), ("ldo", C.c_int32),
+        ("out_f16", C.c_void_p), ("ldh", C.c_int32), ("out_planes", C.c_int32), ("out_plane_stride", C.c_int64),
+        ("block_n", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+EPI_F32, EPI_F16, EPI_GEGLU = 0, 1, 2
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the sources changed and nvcc is available) the native library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    from . import _build
+    path = _build.build()
+    if not os.path.exists(path):
+        raise DfuError(f"{path} missing: the CUDA extension is required (no fallback)")
+    L = C.CDLL(path)
+    L.dfu_version.restype = C.c_int
+    L.dfu_last_error.restype = C.c_char_p
+    L.dfu_num_sms.restype = C.c_int
+    L.dfu_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
+    L.dfu_gemm.restype = C.c_int
+    L.dfu_gemm_workspace.argtypes = [C.POINTER(Gemm)]
+    L.dfu_gemm_workspace.restype = C.c_size_t
+    _declare_rest(L)
+    _lib = L
+    return L
+
+
+def _declare_rest(L):
+    """argtypes for the non-GEMM entry points (kept in one table so tests can check header <-> binding)."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+# name -> (restype, argtypes); filled as entry points are added (see include/diffute_b200.h)
+SIGNATURES = {}
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().dfu_last_error().decode(errors="replace")
+        raise DfuError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,562 @@
+// diffute_b200 — tcgen05 contraction core (linear / 1x1 / 3x3 implicit-GEMM conv) for sm_100a.
+//
+// One CTA computes one 128 x block_n output tile over a K-range (split-K slice):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 2-D for matrices / weights, 4-D NHWC boxes for conv taps;
+//              the halo and the stride-2 / asymmetric padding come from TMA out-of-bounds zero fill)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp32 accumulate in TMEM)
+//   warps 2-5: epilogue, tcgen05.ld TMEM -> registers -> fused bias / time-embedding / residual / GEGLU /
+//              fp16-split stores, 128-bit wide.
+// Operands live in shared memory in the 128-byte-swizzled K-major layout that TMA writes and the UMMA
+// descriptors read; a `stages`-deep full/empty mbarrier ring connects producer and issuer.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfu {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KiB smem slot for A (box may fill fewer rows)
+
+struct GroupDev {
+  int a_mode, ntaps, nchunks, a_plane, b_plane, kb_per_pass;
+  int8_t dn[9], dy[9], dx[9];
+};
+
+struct EpiParams {
+  int M, N;
+  int epi;
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  int rowvec_ld, rows_per_sample;
+  const float* residual;
+  int ldr;
+  float* out_f32;
+  int ldo;
+  __half* out_f16;
+  int ldh;
+  int out_planes;
+  long long out_plane_stride;
+};
+
+struct GemmKernelParams {
+  int block_n, tiles_m, tiles_n, splits, stages, total_kb;
+  int ngroups, npass;
+  GroupDev g[2];
+  int conv, B, H, W, bw, bh, bn, tiles_x, tiles_y;
+  uint32_t a_tx_bytes[2];  // bytes one A box delivers (per group)
+  uint32_t b_tx_bytes;
+  uint32_t tmem_cols;
+  float* ws;
+  EpiParams e;
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared epilogue: 32 consecutive columns [n, n+32) of output row m
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_f16x8(__half* dst, const float* v, bool lo_plane, __half* dst_lo) {
+  __align__(16) __half h[8];
+  __align__(16) __half l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(v[i]);
+    l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+  }
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+  if (lo_plane) *reinterpret_cast<uint4*>(dst_lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+__device__ __forceinline__ void epilogue_chunk32(const EpiParams& e, int m, int n, float (&v)[32]) {
+  if (e.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= e.alpha;
+  }
+  if (e.bias) {
+    const float4* b = reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = __ldg(b + i);
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (e.rowvec) {
+    const float4* b =
+        reinterpret_cast<const float4*>(e.rowvec + static_cast<size_t>(m / e.rows_per_sample) * e.rowvec_ld + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = __ldg(b + i);
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (e.epi == DFU_EPI_GEGLU) {
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = v[i] * gelu_erf_f(v[16 + i]);
+    __half* dst = e.out_f16 + static_cast<size_t>(m) * e.ldh + (n >> 1);
+    store_f16x8(dst, o, e.out_planes > 1, dst + e.out_plane_stride);
+    store_f16x8(dst + 8, o + 8, e.out_planes > 1, dst + e.out_plane_stride + 8);
+    return;
+  }
+  if (e.residual) {
+    const float4* r = reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(m) * e.ldr + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = r[i];
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (e.epi == DFU_EPI_F32) {
+    float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    __half* dst = e.out_f16 + static_cast<size_t>(m) * e.ldh + n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      store_f16x8(dst + 8 * i, v + 8 * i, e.out_planes > 1, dst + e.out_plane_stride + 8 * i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * 128u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates -------------------------------------------------------------------
+  int bid = blockIdx.x;
+  const int tn = bid % p.tiles_n;
+  bid /= p.tiles_n;
+  const int tm = bid % p.tiles_m;
+  const int split = bid / p.tiles_m;
+  const int kb0 = static_cast<int>(static_cast<long long>(p.total_kb) * split / p.splits);
+  const int kb1 = static_cast<int>(static_cast<long long>(p.total_kb) * (split + 1) / p.splits);
+  const int n_tile0 = tn * p.block_n;
+  int m0 = tm * kBlockM, x0 = 0, y0 = 0, img0 = 0;
+  if (p.conv) {
+    int t = tm;
+    x0 = (t % p.tiles_x) * p.bw;
+    t /= p.tiles_x;
+    y0 = (t % p.tiles_y) * p.bh;
+    img0 = (t / p.tiles_y) * p.bn;
+  }
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.ngroups > 1) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====================================================================
+    if (lane == 0) {
+      const int kbg0 = p.g[0].kb_per_pass * p.npass;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int r = kb, gi = 0;
+        if (r >= kbg0) {
+          r -= kbg0;
+          gi = 1;
+        }
+        const GroupDev& G = p.g[gi];
+        const int pass = r / G.kb_per_pass;
+        r -= pass * G.kb_per_pass;
+        const int tap = r / G.nchunks;
+        const int chunk = r - tap * G.nchunks;
+        const int a_sel = (pass == 1) ? G.a_plane : 0;
+        const int b_sel = (pass == 2) ? G.b_plane : 0;
+        const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
+        const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * stage_bytes;
+        uint8_t* sB = sA + kABytes;
+        mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes[gi] + p.b_tx_bytes);
+        if (G.a_mode == 0) {
+          tma_load_2d(sA, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
+        } else {
+          tma_load_4d(sA, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
+                      img0 + G.dn[tap] + a_sel);
+        }
+        tma_load_2d(sB, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, n_tile0 + b_sel);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =======================================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sB = sA + kABytes;
+        const uint64_t adesc = umma_desc_sw128(sA);
+        const uint64_t bdesc = umma_desc_sw128(sB);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+          umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem slot when the MMAs above have read it
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps (2..5) =============================================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    int m;
+    bool valid;
+    if (p.conv) {
+      const int ix = r % p.bw;
+      const int t = r / p.bw;
+      const int iy = t % p.bh;
+      const int in = t / p.bh;
+      const int x = x0 + ix, y = y0 + iy, img = img0 + in;
+      valid = (in < p.bn) && (x < p.W) && (y < p.H) && (img < p.B);
+      m = (img * p.H + y) * p.W + x;
+    } else {
+      m = m0 + r;
+      valid = m < p.e.M;
+    }
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < p.block_n; c += 32) {
+      uint32_t raw[32];
+      tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
+      tmem_ld_wait();
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        const int n = n_tile0 + c;
+        if (p.splits > 1) {
+          float4* o = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + m) * p.e.N + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          epilogue_chunk32(p.e, m, n, v);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// split-K: sum the fp32 partial tiles in a fixed order (deterministic), then the fused epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
+  const int chunks_per_row = e.N / 32;
+  const long long total = static_cast<long long>(e.M) * chunks_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / chunks_per_row);
+    const int n = static_cast<int>(idx % chunks_per_row) * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(s) * e.M + m) * e.N + n);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 t = src[i];
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+      }
+    }
+    epilogue_chunk32(e, m, n, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  int block_n, splits, stages, tiles_m, tiles_n, total_kb;
+  int bw, bh, bn, tiles_x, tiles_y;
+  size_t ws_bytes;
+  size_t smem_bytes;
+};
+
+static int plan_gemm(const DfuGemm* d, Plan* pl) {
+  DFU_REQUIRE(d->m > 0 && d->n > 0, "gemm: empty problem m=%d n=%d", d->m, d->n);
+  DFU_REQUIRE(d->ngroups == 1 || d->ngroups == 2, "gemm: ngroups must be 1 or 2");
+  DFU_REQUIRE(d->npass == 1 || d->npass == 3, "gemm: npass must be 1 or 3");
+  DFU_REQUIRE(d->n % 32 == 0, "gemm: n=%d must be a multiple of 32", d->n);
+  int total_kb = 0;
+  for (int g = 0; g < d->ngroups; ++g) {
+    const DfuGemmOperand& o = d->g[g];
+    DFU_REQUIRE(o.ntaps >= 1 && o.ntaps <= 9, "gemm: ntaps=%d", o.ntaps);
+    DFU_REQUIRE(o.k_per_tap > 0 && o.k_per_tap % kBlockK == 0, "gemm: k_per_tap=%d must be a multiple of 64",
+                o.k_per_tap);
+    DFU_REQUIRE(o.a_mode == 0 || (o.a_mode == 1 && d->conv), "gemm: image operand needs conv=1");
+    DFU_REQUIRE(!(o.a_mode == 0 && o.ntaps != 1), "gemm: matrix operand must have ntaps=1");
+    DFU_REQUIRE(!(o.a_mode == 1 && o.a_c != o.k_per_tap), "gemm: a_c must equal k_per_tap");
+    total_kb += o.ntaps * (o.k_per_tap / kBlockK) * d->npass;
+  }
+  pl->total_kb = total_kb;
+  if (d->conv) {
+    DFU_REQUIRE(d->m == d->B * d->H * d->W, "gemm: conv m=%d != B*H*W", d->m);
+    pl->bw = d->W < 128 ? d->W : 128;
+    pl->bh = 1;
+    pl->bn = 1;
+    if (d->W < 128) {
+      int bh = 128 / d->W;
+      if (bh > d->H) bh = d->H;
+      pl->bh = bh;
+      if (bh == d->H) {
+        int bn = 128 / (d->H * d->W);
+        if (bn < 1) bn = 1;
+        if (bn > d->B) bn = d->B;
+        pl->bn = bn;
+      }
+    }
+    pl->tiles_x = (d->W + pl->bw - 1) / pl->bw;
+    pl->tiles_y = (d->H + pl->bh - 1) / pl->bh;
+    pl->tiles_m = pl->tiles_x * pl->tiles_y * ((d->B + pl->bn - 1) / pl->bn);
+  } else {
+    pl->bw = pl->bh = pl->bn = pl->tiles_x = pl->tiles_y = 0;
+    pl->tiles_m = (d->m + kBlockM - 1) / kBlockM;
+  }
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  int bn_ = d->block_n;
+  if (bn_ <= 0) {
+    const int cands[] = {256, 160, 128, 96, 64, 32};
+    bn_ = 0;
+    // widest tile that still leaves enough CTAs; otherwise the widest that divides n
+    for (int c : cands)
+      if (d->n % c == 0 && pl->tiles_m * (d->n / c) >= sms - 28) {
+        bn_ = c;
+        break;
+      }
+    if (!bn_)
+      for (int c : cands)
+        if (d->n % c == 0 && c <= 160) {
+          bn_ = c;
+          break;
+        }
+    if (!bn_) bn_ = 32;
+  }
+  DFU_REQUIRE(bn_ % 32 == 0 && bn_ <= 256 && d->n % bn_ == 0, "gemm: bad block_n=%d for n=%d", bn_, d->n);
+  pl->block_n = bn_;
+  pl->tiles_n = d->n / bn_;
+  int splits = d->splits;
+  if (splits <= 0) {
+    const int tiles = pl->tiles_m * pl->tiles_n;
+    splits = 1;
+    if (tiles < sms * 3 / 4) {
+      splits = (sms + tiles - 1) / tiles;
+      const int max_by_k = total_kb / 4 > 0 ? total_kb / 4 : 1;
+      if (splits > max_by_k) splits = max_by_k;
+      if (splits > 32) splits = 32;
+    }
+  }
+  DFU_REQUIRE(splits >= 1 && splits <= total_kb, "gemm: bad splits=%d (k-blocks %d)", splits, total_kb);
+  pl->splits = splits;
+  pl->ws_bytes = splits > 1 ? static_cast<size_t>(splits) * d->m * d->n * sizeof(float) : 0;
+  int stages = d->stages;
+  const size_t stage_bytes = kABytes + static_cast<size_t>(bn_) * 128;
+  if (stages <= 0) {
+    stages = bn_ > 160 ? 4 : 3;  // <=160: ~108 KiB -> two CTAs per SM overlap epilogue and main loop
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  pl->stages = stages;
+  pl->smem_bytes = stages * stage_bytes + 1024;
+  DFU_REQUIRE(pl->smem_bytes <= 227 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
+  return DFU_OK;
+}
+
+static int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& pl, CUtensorMap* mA, CUtensorMap* mB,
+                        uint32_t* a_tx) {
+  int rc;
+  if (o.a_mode == 0) {
+    uint64_t dims[2] = {static_cast<uint64_t>(o.ntaps) * o.k_per_tap, static_cast<uint64_t>(o.a_rows)};
+    uint64_t str[1] = {static_cast<uint64_t>(o.a_ld) * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    rc = make_tmap_f16(mA, o.a, 2, dims, str, box);
+    *a_tx = kABytes;
+  } else {
+    uint64_t dims[4] = {static_cast<uint64_t>(o.a_c), static_cast<uint64_t>(o.a_w), static_cast<uint64_t>(o.a_h),
+                        static_cast<uint64_t>(o.a_rows)};
+    uint64_t str[3] = {static_cast<uint64_t>(o.a_c) * 2, static_cast<uint64_t>(o.a_c) * o.a_w * 2,
+                       static_cast<uint64_t>(o.a_c) * o.a_w * o.a_h * 2};
+    uint32_t box[4] = {kBlockK, static_cast<uint32_t>(pl.bw), static_cast<uint32_t>(pl.bh),
+                       static_cast<uint32_t>(pl.bn)};
+    rc = make_tmap_f16(mA, o.a, 4, dims, str, box);
+    *a_tx = static_cast<uint32_t>(pl.bw * pl.bh * pl.bn) * kBlockK * 2;
+  }
+  if (rc) return rc;
+  uint64_t bdims[2] = {static_cast<uint64_t>(o.b_ld), static_cast<uint64_t>(o.b_rows)};
+  uint64_t bstr[1] = {static_cast<uint64_t>(o.b_ld) * 2};
+  uint32_t bbox[2] = {kBlockK, static_cast<uint32_t>(pl.block_n)};
+  DFU_REQUIRE(o.b_ld == o.ntaps * o.k_per_tap, "gemm: b_ld=%d != ntaps*k_per_tap", o.b_ld);
+  return make_tmap_f16(mB, o.b, 2, bdims, bstr, bbox);
+}
+
+static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
+  Plan pl;
+  int rc = plan_gemm(d, &pl);
+  if (rc) return rc;
+  if (pl.splits > 1) {
+    if (!d->workspace || d->workspace_bytes < pl.ws_bytes) {
+      set_error("gemm: split-K needs %zu workspace bytes, got %zu", pl.ws_bytes, d->workspace_bytes);
+      return DFU_ERR_WORKSPACE;
+    }
+  }
+  DFU_REQUIRE(d->epi >= 0 && d->epi <= 2, "gemm: bad epi");
+  if (d->epi == DFU_EPI_F32) DFU_REQUIRE(d->out_f32 && d->ldo % 4 == 0, "gemm: out_f32/ldo");
+  if (d->epi != DFU_EPI_F32) DFU_REQUIRE(d->out_f16 && d->ldh % 8 == 0, "gemm: out_f16/ldh");
+  if (d->residual) DFU_REQUIRE(d->ldr % 4 == 0, "gemm: ldr");
+  if (d->rowvec) DFU_REQUIRE(d->rows_per_sample > 0 && d->rowvec_ld % 4 == 0, "gemm: rowvec");
+
+  CUtensorMap mA[2], mB[2];
+  GemmKernelParams p;
+  memset(&p, 0, sizeof(p));
+  for (int g = 0; g < d->ngroups; ++g) {
+    rc = encode_group(d, d->g[g], pl, &mA[g], &mB[g], &p.a_tx_bytes[g]);
+    if (rc) return rc;
+    const DfuGemmOperand& o = d->g[g];
+    GroupDev& G = p.g[g];
+    G.a_mode = o.a_mode;
+    G.ntaps = o.ntaps;
+    G.nchunks = o.k_per_tap / kBlockK;
+    G.a_plane = o.a_plane;
+    G.b_plane = o.b_plane;
+    G.kb_per_pass = o.ntaps * G.nchunks;
+    for (int t = 0; t < 9; ++t) {
+      G.dn[t] = o.tap_dn[t];
+      G.dy[t] = o.tap_dy[t];
+      G.dx[t] = o.tap_dx[t];
+    }
+  }
+  if (d->ngroups == 1) {
+    mA[1] = mA[0];
+    mB[1] = mB[0];
+  }
+  p.block_n = pl.block_n;
+  p.tiles_m = pl.tiles_m;
+  p.tiles_n = pl.tiles_n;
+  p.splits = pl.splits;
+  p.stages = pl.stages;
+  p.total_kb = pl.total_kb;
+  p.ngroups = d->ngroups;
+  p.npass = d->npass;
+  p.conv = d->conv;
+  p.B = d->B;
+  p.H = d->H;
+  p.W = d->W;
+  p.bw = pl.bw;
+  p.bh = pl.bh;
+  p.bn = pl.bn;
+  p.tiles_x = pl.tiles_x;
+  p.tiles_y = pl.tiles_y;
+  p.b_tx_bytes = static_cast<uint32_t>(pl.block_n) * kBlockK * 2;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(pl.block_n)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.ws = static_cast<float*>(d->workspace);
+  EpiParams& e = p.e;
+  e.M = d->m;
+  e.N = d->n;
+  e.epi = d->epi;
+  e.alpha = d->alpha;
+  e.bias = d->bias;
+  e.rowvec = d->rowvec;
+  e.rowvec_ld = d->rowvec_ld;
+  e.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  e.residual = d->residual;
+  e.ldr = d->ldr;
+  e.out_f32 = d->out_f32;
+  e.ldo = d->ldo;
+  e.out_f16 = static_cast<__half*>(d->out_f16);
+  e.ldh = d->ldh;
+  e.out_planes = d->out_planes > 0 ? d->out_planes : 1;
+  e.out_plane_stride = d->out_plane_stride;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
+  gemm_tc_kernel<<<grid, kGemmThreads, pl.smem_bytes, stream>>>(mA[0], mB[0], mA[1], mB[1], p);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  if (pl.splits > 1) {
+    const long long total = static_cast<long long>(d->m) * (d->n / 32);
+    int blocks = static_cast<int>((total + 255) / 256);
+    const int cap = num_sms() > 0 ? num_sms() * 8 : 1184;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, pl.splits, e);
+    DFU_CHECK_CUDA(cudaGetLastError());
+  }
+  return DFU_OK;
+}
+
+}  // namespace dfu
+
+extern "C" {
+int dfu_gemm(const DfuGemm* desc, void* stream) {
+  if (!desc) {
+    dfu::set_error("gemm: null descriptor");
+    return DFU_ERR_INVALID;
+  }
+  return dfu::run_gemm(desc, static_cast<cudaStream_t>(stream));
+}
+size_t dfu_gemm_workspace(const DfuGemm* desc) {
+  dfu::Plan pl;
+  if (!desc || dfu::plan_gemm(desc, &pl)) return 0;
+  return pl.ws_bytes;
+}
+}

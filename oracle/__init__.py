@@ -1,0 +1,25 @@
+"""CPU oracle for the DiffUTE sampling hot path (TEST INFRASTRUCTURE ONLY).
+
+This package is a plain-PyTorch fp32 restatement of the third-party diffusers
+modules that chenhaoxing/DiffUTE calls on its sampling path
+(reference call sites: app.ipynb:772-819, train_diffute_v1.py:875-913):
+
+    UNet2DConditionModel.forward      -> oracle.unet.UNetOracle
+    AutoencoderKL.encode/decode       -> oracle.vae.VAEOracle
+    DDIMScheduler / DDPMScheduler     -> oracle.schedulers
+
+diffusers itself is not vendored under /root/reference, is not pinned by the
+reference (requirements.txt:1-8; floor "0.15.0.dev0" at train_diffute_v1.py:63)
+and is not installable offline, so the algorithm is restated from its published
+architecture.  PARITY PINS: exact parameter totals
+(UNet 865,925,124; VAE 83,653,863) and six upstream scheduler known-answer
+constants (tests/test_oracle_*.py).  UNet/VAE *outputs* have no golden vectors
+in the reference (it has no tests at all): "parity unpinned" for those.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package.  The product (diffute_b200/) never does.
+"""
+from .unet import UNetOracle, SD2_INPAINT_UNET_CONFIG  # noqa: F401
+from .vae import VAEOracle, SD2_VAE_CONFIG, DiagonalGaussian  # noqa: F401
+from .schedulers import DDIMOracle, DDPMOracle, SD2_SCHEDULER_CONFIG  # noqa: F401
+from .sampling import sample_loop  # noqa: F401
