@@ -77,7 +77,22 @@ def _declare_rest(L):
 
 
 # name -> (restype, argtypes); filled as entry points are added (see include/diffute_b200.h)
-SIGNATURES = {}
+_vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+SIGNATURES = {
+    "dfu_groupnorm_workspace": (_sz, [_i, _i, _i, _i]),
+    "dfu_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dfu_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _i, _i64, _vp]),
+    "dfu_cast_f16": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
+    "dfu_timestep_embedding": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
+    "dfu_gemv": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "dfu_conv_small_in": (_i, [_vp, _i, _i64, _vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp,
+                               _vp]),
+    "dfu_conv_small_out": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "dfu_axpbypcz": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64, _vp]),
+    "dfu_gaussian_sample": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "dfu_softmax_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _i, _i, _i64, _vp]),
+    "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp]),
+}
 
 
 def check(rc: int, what: str = "") -> None:

@@ -414,7 +414,7 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
   if (stages > kMaxStages) stages = kMaxStages;
   pl->stages = stages;
   pl->smem_bytes = stages * stage_bytes + 1024;
-  DFU_REQUIRE(pl->smem_bytes <= 227 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
+  DFU_REQUIRE(pl->smem_bytes <= 226 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
   return DFU_OK;
 }
 
@@ -527,7 +527,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;

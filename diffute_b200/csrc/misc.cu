@@ -1,0 +1,412 @@
+// diffute_b200 — small fp32 CUDA-core kernels around the tensor-core path: timestep embedding, batched GEMV
+// (time-embedding MLP and the 22 time_emb_proj layers in one launch), the few-channel edge convolutions
+// (conv_in 9->320, conv_out 320->4 with the scheduler step fused, VAE 3->128 / 128->3 / 4->512 / 512->8 and the
+// 1x1 quant convs), row softmax for the single-head VAE attention and the scheduler updates.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfu {
+
+// ---------------------------------------------------------------------------------------------
+// diffusers `Timesteps`: emb[b, :half] = cos(t * f_i), emb[b, half:] = sin(t * f_i)  (flip_sin_to_cos=True)
+// f_i = exp(-ln(10000) * i / (half - freq_shift))
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int B, int dim, int flip_sin_to_cos,
+                                      float freq_shift, float* __restrict__ out) {
+  const int half = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+    const int b = i / half, k = i % half;
+    const float f = expf(-9.210340371976184f * static_cast<float>(k) / (static_cast<float>(half) - freq_shift));
+    const float arg = t[b] * f;
+    float s, c;
+    sincosf(arg, &s, &c);
+    float* o = out + static_cast<size_t>(b) * dim;
+    if (flip_sin_to_cos) {
+      o[k] = c;
+      o[half + k] = s;
+    } else {
+      o[k] = s;
+      o[half + k] = c;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[b, n] = act_out( bias[n] + sum_k W[n, k] * act_in(x[b, k]) ), fp32 weights streamed once with 128-bit loads.
+// One warp per output column n; B <= 16 rows are accumulated together so W is read exactly once.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemvMaxB = 16;
+
+__global__ void __launch_bounds__(256)
+gemv_kernel(const float* __restrict__ x, int B, int K, int ldx, const float* __restrict__ W,
+            const float* __restrict__ bias, int N, int silu_in, int silu_out, float* __restrict__ out, int ldo) {
+  extern __shared__ float xs[];  // [B][K] activated input
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    const int b = i / K, k = i % K;
+    float v = x[static_cast<size_t>(b) * ldx + k];
+    xs[i] = silu_in ? silu_f(v) : v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
+    float acc[kGemvMaxB];
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) acc[b] = 0.f;
+    const float4* w = reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K);
+    for (int q = lane; q < K / 4; q += 32) {
+      const float4 wv = __ldg(w + q);
+#pragma unroll
+      for (int b = 0; b < kGemvMaxB; ++b) {
+        if (b < B) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + b * K + q * 4);
+          acc[b] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) {
+      if (b < B) {
+        float v = warp_sum(acc[b]);
+        if (lane == 0) {
+          v += bias ? bias[n] : 0.f;
+          out[static_cast<size_t>(b) * ldo + n] = silu_out ? silu_f(v) : v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Few-input-channel 3x3 / 1x1 conv: NCHW fp32 in (Cin <= 16, optionally gathered from up to 3 tensors, i.e. the
+// cat([latents, mask, masked_latents]) of app.ipynb:811 is never materialised) -> NHWC fp32 out.  pad = k/2.
+// ---------------------------------------------------------------------------------------------
+struct SmallInSrc {
+  const float* p[3];
+  int c[3];
+  long long bstride[3];  // elements between samples (0 broadcasts one sample to the batch)
+};
+
+__global__ void __launch_bounds__(256)
+conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const float* __restrict__ w,
+                     const float* __restrict__ bias, int Cout, float pre_scale, float* __restrict__ out) {
+  // block: 64 output pixels (consecutive in a row-major walk) x all Cout; patch staged in smem
+  extern __shared__ float sm[];  // [64][Cin*ksz*ksz]
+  const int kk = ksz * ksz;
+  const int K = Cin * kk;
+  const int pad = ksz / 2;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * 64;
+  const long long npix = static_cast<long long>(B) * H * W;
+  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
+    const int pl = i / K, k = i % K;
+    const long long pix = pix0 + pl;
+    float v = 0.f;
+    if (pix < npix) {
+      const int c = k / kk, t = k % kk;
+      const int ky = t / ksz, kx = t % ksz;
+      const int x = static_cast<int>(pix % W);
+      const int y = static_cast<int>((pix / W) % H);
+      const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+      const int iy = y + ky - pad, ix = x + kx - pad;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        int cc = c, si = 0;
+        if (cc >= s.c[0]) { cc -= s.c[0]; si = 1; if (cc >= s.c[1]) { cc -= s.c[1]; si = 2; } }
+        v = s.p[si][b * s.bstride[si] + (static_cast<long long>(cc) * H + iy) * W + ix] * pre_scale;
+      }
+    }
+    sm[i] = v;
+  }
+  __syncthreads();
+  // thread -> (pixel pl, output channel co) with co fastest for coalesced NHWC stores
+  for (int i = threadIdx.x; i < 64 * Cout; i += blockDim.x) {
+    const int pl = i / Cout, co = i % Cout;
+    const long long pix = pix0 + pl;
+    if (pix >= npix) continue;
+    const float* wr = w + static_cast<size_t>(co) * K;
+    const float* xr = sm + pl * K;
+    float acc = bias ? bias[co] : 0.f;
+    for (int k = 0; k < K; ++k) acc += wr[k] * xr[k];
+    out[pix * Cout + co] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Few-output-channel conv: NHWC fp32 in (Cin multiple of 128... any multiple of 4) -> NCHW fp32 out (Cout <= 8),
+// optional fused second 1x1 conv on the result (VAE quant_conv), optional fused scheduler update
+// (x' = cx * x + ce * eps) so the UNet's conv_out writes the next latents directly.
+// One warp per output pixel; lanes split the input channels.
+// ---------------------------------------------------------------------------------------------
+struct SmallOut {
+  const float* x;      // [B,H,W,Cin]
+  int B, H, W, Cin, ksz, Cout;
+  const float* w;      // [Cout][ksz*ksz][Cin]  (repacked: channels innermost)
+  const float* bias;
+  const float* w2;     // optional [Cout2][Cout] 1x1 applied afterwards
+  const float* b2;
+  int Cout2;
+  float* out;          // NCHW [B, Cout(2), H, W]
+  // fused scheduler step (optional): sample/prev are NCHW [B,Cout,H,W]
+  const float* sample;
+  float* prev;
+  const float* coef;   // device [2] = {cx, ce}
+};
+
+__global__ void __launch_bounds__(256) conv_small_out_kernel(SmallOut p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
+  if (warp >= npix) return;
+  const int x = static_cast<int>(warp % p.W);
+  const int y = static_cast<int>((warp / p.W) % p.H);
+  const int b = static_cast<int>(warp / (static_cast<long long>(p.W) * p.H));
+  const int pad = p.ksz / 2;
+  const int kk = p.ksz * p.ksz;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int C4 = p.Cin >> 2;
+  for (int t = 0; t < kk; ++t) {
+    const int iy = y + t / p.ksz - pad, ix = x + t % p.ksz - pad;
+    if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+    const float4* xr = reinterpret_cast<const float4*>(p.x + ((static_cast<size_t>(b) * p.H + iy) * p.W + ix) * p.Cin);
+    for (int q = lane; q < C4; q += 32) {
+      const float4 xv = xr[q];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) {
+        if (co < p.Cout) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(co) * kk + t) * p.Cin) + q);
+          acc[co] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 8; ++co) acc[co] = warp_sum(acc[co]);
+  if (lane == 0) {
+    float v[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) v[co] = (co < p.Cout) ? acc[co] + (p.bias ? p.bias[co] : 0.f) : 0.f;
+    int nout = p.Cout;
+    float o[8];
+    if (p.w2) {
+      nout = p.Cout2;
+      for (int j = 0; j < p.Cout2; ++j) {
+        float a = p.b2 ? p.b2[j] : 0.f;
+        for (int co = 0; co < p.Cout; ++co) a += p.w2[j * p.Cout + co] * v[co];
+        o[j] = a;
+      }
+    } else {
+#pragma unroll
+      for (int co = 0; co < 8; ++co) o[co] = v[co];
+    }
+    const size_t hw = static_cast<size_t>(p.H) * p.W;
+    const size_t base = static_cast<size_t>(b) * nout * hw + static_cast<size_t>(y) * p.W + x;
+    for (int j = 0; j < nout; ++j) {
+      if (p.out) p.out[base + j * hw] = o[j];
+      if (p.prev) p.prev[base + j * hw] = p.coef[0] * p.sample[base + j * hw] + p.coef[1] * o[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise: y = a*x + b*e (+ c*n)   (DDIM eta=0: c = 0;  DDPM: x0/x form pre-collapsed on the host)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+axpbypcz_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ n, float a, float b,
+                float c, float* __restrict__ y, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = a * x[i] + b * e[i];
+    if (n) v += c * n[i];
+    y[i] = v;
+  }
+}
+
+// DiagonalGaussian sample from NCHW moments [B, 2*Cz, h, w]: z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps) * scale
+__global__ void __launch_bounds__(256)
+gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ eps, int B, int Cz, int HW,
+                       float scale, float* __restrict__ z) {
+  const long long total = static_cast<long long>(B) * Cz * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / (static_cast<long long>(Cz) * HW);
+    const long long r = i % (static_cast<long long>(Cz) * HW);
+    const float mean = moments[b * 2 * Cz * HW + r];
+    float v = mean;
+    if (eps) {
+      float lv = moments[b * 2 * Cz * HW + static_cast<long long>(Cz) * HW + r];
+      lv = fminf(fmaxf(lv, -30.f), 20.f);
+      v += expf(0.5f * lv) * eps[i];
+    }
+    z[i] = v * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row softmax: fp32 scores [rows, n] (scaled by `scale`) -> fp16 operand planes [planes][rows][ldp]
+// (single-head d=512 VAE attention; the UNet uses the fused flash kernel in attn.cu)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, int rows, int n, int lds, float scale, __half* __restrict__ p16,
+                    int ldp, int planes, long long plane_stride) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  __shared__ float red[32];
+  const float* sr = s + static_cast<size_t>(row) * lds;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf((sr[i] - mx) * scale);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  __half* pr = p16 + static_cast<size_t>(row) * ldp;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = expf((sr[i] - mx) * scale) * inv;
+    const __half h = __float2half_rn(v);
+    pr[i] = h;
+    if (planes > 1) pr[plane_stride + i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// fp16 [planes][rows][cols] -> transposed [planes][cols][rows] (V^T for the VAE attention's P*V GEMM)
+__global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, long long in_plane,
+                                     __half* __restrict__ out, long long out_plane) {
+  __shared__ __half tile[32][33];
+  const __half* src = in + blockIdx.z * in_plane;
+  __half* dst = out + blockIdx.z * out_plane;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[static_cast<size_t>(r) * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[static_cast<size_t>(c) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+static int ew_grid2(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace dfu
+
+using namespace dfu;
+
+extern "C" {
+
+int dfu_timestep_embedding(const float* t, int B, int dim, int flip_sin_to_cos, float freq_shift, float* out,
+                           void* stream) {
+  DFU_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: B=%d dim=%d", B, dim);
+  timestep_embed_kernel<<<ew_grid2(static_cast<long long>(B) * dim / 2, 128), 128, 0,
+                          static_cast<cudaStream_t>(stream)>>>(t, B, dim, flip_sin_to_cos, freq_shift, out);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float* bias, int N, int silu_in,
+             int silu_out, float* out, int ldo, void* stream) {
+  DFU_REQUIRE(B >= 1 && B <= kGemvMaxB, "gemv: B=%d (max %d)", B, kGemvMaxB);
+  DFU_REQUIRE(K % 4 == 0, "gemv: K=%d", K);
+  const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
+  DFU_REQUIRE(smem <= 96 * 1024, "gemv: B*K too large");
+  static bool attr = false;
+  if (!attr) {
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  int blocks = (N + 7) / 8;
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 4;
+  if (blocks > cap) blocks = cap;
+  gemv_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, B, K, ldx, W, bias, N, silu_in, silu_out,
+                                                                       out, ldo);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* src1, int c1, int64_t bstride1,
+                      const float* src2, int c2, int64_t bstride2, int B, int H, int W, int ksz, const float* w,
+                      const float* bias, int Cout, float pre_scale, float* out, void* stream) {
+  const int Cin = c0 + c1 + c2;
+  DFU_REQUIRE(src0 && Cin > 0 && Cin <= 16 && (ksz == 1 || ksz == 3), "conv_small_in: Cin=%d ksz=%d", Cin, ksz);
+  SmallInSrc s;
+  s.p[0] = src0; s.p[1] = src1; s.p[2] = src2;
+  s.c[0] = c0; s.c[1] = c1; s.c[2] = c2;
+  s.bstride[0] = bstride0; s.bstride[1] = bstride1; s.bstride[2] = bstride2;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const int blocks = static_cast<int>((npix + 63) / 64);
+  const size_t smem = 64ull * Cin * ksz * ksz * sizeof(float);
+  conv_small_in_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(s, B, H, W, Cin, ksz, w, bias, Cout,
+                                                                                pre_scale, out);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, const float* w, const float* bias,
+                       int Cout, const float* w2, const float* b2, int Cout2, float* out, const float* sample,
+                       float* prev, const float* coef, void* stream) {
+  DFU_REQUIRE(Cout >= 1 && Cout <= 8 && Cin % 4 == 0 && (ksz == 1 || ksz == 3), "conv_small_out: Cout=%d Cin=%d", Cout,
+              Cin);
+  DFU_REQUIRE(!w2 || (Cout2 >= 1 && Cout2 <= 8), "conv_small_out: Cout2=%d", Cout2);
+  DFU_REQUIRE(out || prev, "conv_small_out: no output");
+  DFU_REQUIRE(!prev || (sample && coef), "conv_small_out: fused step needs sample and coef");
+  SmallOut p;
+  p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.ksz = ksz; p.Cout = Cout;
+  p.w = w; p.bias = bias; p.w2 = w2; p.b2 = b2; p.Cout2 = Cout2; p.out = out;
+  p.sample = sample; p.prev = prev; p.coef = coef;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long blocks = (npix * 32 + 255) / 256;
+  conv_small_out_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_axpbypcz(const float* x, const float* e, const float* n, float a, float b, float c, float* y, int64_t total,
+                 void* stream) {
+  axpbypcz_kernel<<<ew_grid2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, e, n, a, b, c, y, total);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_gaussian_sample(const float* moments, const float* eps, int B, int Cz, int HW, float scale, float* z,
+                        void* stream) {
+  gaussian_sample_kernel<<<ew_grid2(static_cast<long long>(B) * Cz * HW, 256), 256, 0,
+                           static_cast<cudaStream_t>(stream)>>>(moments, eps, B, Cz, HW, scale, z);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void* p16, int ldp, int planes,
+                     int64_t plane_stride, void* stream) {
+  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, rows, n, lds, scale,
+                                                                         static_cast<__half*>(p16), ldp, planes,
+                                                                         plane_stride);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int64_t in_plane, void* out, int64_t out_plane,
+                      void* stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, planes), block(32, 8);
+  transpose_f16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(in), rows, cols, in_plane, static_cast<__half*>(out), out_plane);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+}

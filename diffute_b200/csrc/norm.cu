@@ -1,0 +1,324 @@
+// diffute_b200 — memory-bound normalisation / cast kernels (GroupNorm+SiLU, LayerNorm, fp32 -> fp16 operand casts).
+//
+// All activations are NHWC fp32 (the residual stream); these kernels read them once with 128-bit loads and write
+// the 16-bit (hi / lo) operand planes the tcgen05 contraction core consumes, so the fp32 -> fp16 cast, the
+// activation, the skip concat, the nearest-2x upsample and the stride-2 space-to-depth split never cost a pass
+// of their own.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfu {
+
+// =============================================================================================
+// GroupNorm statistics: per (sample, pixel-chunk, group) partial sum / sum of squares
+//   grid (chunks, B), block (C/4, TY).  Thread (tx, ty) owns channel quad tx for pixels ty, ty+TY, ...
+// =============================================================================================
+struct GnSrc {
+  const float* src0;
+  const float* src1;  // optional second tensor of a channel concat ([h, skip] in the up blocks)
+  int C0, C1;         // channels of each source
+  int HW;
+};
+
+__device__ __forceinline__ float4 gn_load(const GnSrc& s, int b, int pix, int cq) {
+  const int c = cq * 4;
+  if (c < s.C0) return *reinterpret_cast<const float4*>(s.src0 + (static_cast<size_t>(b) * s.HW + pix) * s.C0 + c);
+  return *reinterpret_cast<const float4*>(s.src1 + (static_cast<size_t>(b) * s.HW + pix) * s.C1 + (c - s.C0));
+}
+
+__global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial) {
+  extern __shared__ float sm[];  // [2][C]
+  const int C = s.C0 + s.C1;
+  const int cpg = C / groups;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, s.HW);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < 2 * C; i += nthr) sm[i] = 0.f;
+  __syncthreads();
+  float sx[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const float4 v = gn_load(s, b, p, threadIdx.x);
+    sx[0] += v.x; sq[0] += v.x * v.x;
+    sx[1] += v.y; sq[1] += v.y * v.y;
+    sx[2] += v.z; sq[2] += v.z * v.z;
+    sx[3] += v.w; sq[3] += v.w * v.w;
+  }
+  const int c = threadIdx.x * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&sm[c + i], sx[i]);
+    atomicAdd(&sm[C + c + i], sq[i]);
+  }
+  __syncthreads();
+  if (tid < groups) {
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      a += sm[tid * cpg + i];
+      q += sm[C + tid * cpg + i];
+    }
+    partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * groups + tid] = make_float2(a, q);
+  }
+}
+
+// =============================================================================================
+// GroupNorm apply (+SiLU) -> fp16 operand planes (and optionally an fp32 copy and a raw-cast operand)
+// =============================================================================================
+struct GnApply {
+  GnSrc s;
+  int groups;
+  int pix_per_cta;
+  int nchunks;            // partial chunks per sample (gridDim.x of the stats launch)
+  const float2* partial;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int silu;
+  __half* out16;          // [planes][B][HW][C] or null
+  int planes;
+  long long plane_stride;
+  float* out32;           // optional fp32 [B][HW][C] (feeds the tiny fp32 output convs)
+  __half* raw16;          // optional raw (un-normalised) cast of the same input, same layout as out16
+};
+
+__device__ __forceinline__ void store_split4(__half* dst, long long plane_stride, int planes, float4 v) {
+  __align__(8) __half h[4];
+  h[0] = __float2half_rn(v.x); h[1] = __float2half_rn(v.y); h[2] = __float2half_rn(v.z); h[3] = __float2half_rn(v.w);
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+  if (planes > 1) {
+    __align__(8) __half l[4];
+    l[0] = __float2half_rn(v.x - __half2float(h[0]));
+    l[1] = __float2half_rn(v.y - __half2float(h[1]));
+    l[2] = __float2half_rn(v.z - __half2float(h[2]));
+    l[3] = __float2half_rn(v.w - __half2float(h[3]));
+    *reinterpret_cast<uint2*>(dst + plane_stride) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+__global__ void gn_apply_kernel(GnApply a) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = a.s.C0 + a.s.C1;
+  const int cpg = C / a.groups;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < a.groups) {
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < a.nchunks; ++k) {
+      const float2 t = a.partial[(static_cast<size_t>(b) * a.nchunks + k) * a.groups + tid];
+      sum += t.x;
+      sq += t.y;
+    }
+    const double n = static_cast<double>(cpg) * a.s.HW;
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  __syncthreads();
+  const int c = threadIdx.x * 4;
+  float mu[4], rs[4], ga[4], be[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int g = (c + i) / cpg;
+    mu[i] = s_mean[g];
+    rs[i] = s_rstd[g];
+    ga[i] = a.gamma[c + i];
+    be[i] = a.beta[c + i];
+  }
+  const int p0 = blockIdx.x * a.pix_per_cta;
+  const int p1 = min(p0 + a.pix_per_cta, a.s.HW);
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const float4 v = gn_load(a.s, b, p, threadIdx.x);
+    float4 y;
+    y.x = (v.x - mu[0]) * rs[0] * ga[0] + be[0];
+    y.y = (v.y - mu[1]) * rs[1] * ga[1] + be[1];
+    y.z = (v.z - mu[2]) * rs[2] * ga[2] + be[2];
+    y.w = (v.w - mu[3]) * rs[3] * ga[3] + be[3];
+    if (a.silu) {
+      y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+    }
+    const size_t off = (static_cast<size_t>(b) * a.s.HW + p) * C + c;
+    if (a.out16) store_split4(a.out16 + off, a.plane_stride, a.planes, y);
+    if (a.out32) *reinterpret_cast<float4*>(a.out32 + off) = y;
+    if (a.raw16) store_split4(a.raw16 + off, a.plane_stride, a.planes, v);
+  }
+}
+
+// =============================================================================================
+// LayerNorm over the channel dim of [M, C] tokens -> fp16 operand planes.  One warp per token, two-pass in registers.
+// =============================================================================================
+constexpr int kLnMaxQuads = 10;  // C <= 1280
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out16, int planes,
+                 long long plane_stride) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int C4 = C >> 2;
+  const float4* row = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
+  float4 v[kLnMaxQuads];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxQuads; ++i) {
+    const int q = lane + 32 * i;
+    if (q < C4) {
+      v[i] = row[q];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxQuads; ++i) {
+    const int q = lane + 32 * i;
+    if (q < C4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxQuads; ++i) {
+    const int q = lane + 32 * i;
+    if (q < C4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      store_split4(out16 + static_cast<size_t>(warp) * C + q * 4, plane_stride, planes, y);
+    }
+  }
+}
+
+// =============================================================================================
+// fp32 NHWC -> fp16 operand casts.  mode 0: same geometry; 1: nearest 2x upsample; 2: space-to-depth (stride-2 conv)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+cast_kernel(const float* __restrict__ x, int B, int H, int W, int C, int mode, __half* __restrict__ out, int planes,
+            long long plane_stride) {
+  const int C4 = C >> 2;
+  const long long total = static_cast<long long>(B) * H * W * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % C4);
+    long long t = i / C4;
+    const int xw = static_cast<int>(t % W);
+    t /= W;
+    const int y = static_cast<int>(t % H);
+    const int b = static_cast<int>(t / H);
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    if (mode == 0) {
+      store_split4(out + i * 4, plane_stride, planes, v);
+    } else if (mode == 1) {
+      const int H2 = 2 * H, W2 = 2 * W;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t o = ((static_cast<size_t>(b) * H2 + 2 * y + dy) * W2 + 2 * xw + dx) * C + cq * 4;
+          store_split4(out + o, plane_stride, planes, v);
+        }
+    } else {
+      const int Hh = H >> 1, Wh = W >> 1;
+      const int par = (y & 1) * 2 + (xw & 1);
+      const size_t o = (((static_cast<size_t>(par) * B + b) * Hh + (y >> 1)) * Wh + (xw >> 1)) * C + cq * 4;
+      store_split4(out + o, plane_stride, planes, v);
+    }
+  }
+}
+
+static int ew_grid(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace dfu
+
+using namespace dfu;
+
+extern "C" {
+
+size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups) {
+  (void)C;
+  const int ppc = HW >= 65536 ? 256 : (HW >= 4096 ? 64 : (HW >= 1024 ? 32 : 16));
+  const int chunks = (HW + ppc - 1) / ppc;
+  return static_cast<size_t>(B) * chunks * groups * sizeof(float2);
+}
+
+int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, int groups, const float* gamma,
+                  const float* beta, float eps, int silu, void* out16, int planes, int64_t plane_stride, float* out32,
+                  void* raw16, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int C = C0 + C1;
+  DFU_REQUIRE(src0 && C0 > 0 && C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0 || src1), "groupnorm: bad sources");
+  DFU_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: C=%d groups=%d", C, groups);
+  DFU_REQUIRE(C / 4 <= 1024, "groupnorm: C=%d too wide", C);
+  DFU_REQUIRE(out16 || out32, "groupnorm: no output");
+  const size_t need = dfu_groupnorm_workspace(B, HW, C, groups);
+  if (!workspace || workspace_bytes < need) {
+    set_error("groupnorm: workspace %zu < %zu", workspace_bytes, need);
+    return DFU_ERR_WORKSPACE;
+  }
+  const int ppc = HW >= 65536 ? 256 : (HW >= 4096 ? 64 : (HW >= 1024 ? 32 : 16));
+  const int chunks = (HW + ppc - 1) / ppc;
+  const int C4 = C / 4;
+  int ty = 512 / C4;
+  if (ty < 1) ty = 1;
+  if (ty > ppc) ty = ppc;
+  dim3 block(C4, ty), grid(chunks, B);
+  GnSrc s{src0, src1, C0, C1, HW};
+  gn_stats_kernel<<<grid, block, 2 * C * sizeof(float), stream>>>(s, groups, ppc, static_cast<float2*>(workspace));
+  DFU_CHECK_CUDA(cudaGetLastError());
+  GnApply a;
+  a.s = s;
+  a.groups = groups;
+  a.pix_per_cta = ppc;
+  a.nchunks = chunks;
+  a.partial = static_cast<const float2*>(workspace);
+  a.gamma = gamma;
+  a.beta = beta;
+  a.eps = eps;
+  a.silu = silu;
+  a.out16 = static_cast<__half*>(out16);
+  a.planes = planes;
+  a.plane_stride = plane_stride;
+  a.out32 = out32;
+  a.raw16 = static_cast<__half*>(raw16);
+  gn_apply_kernel<<<grid, block, 0, stream>>>(a);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* out16,
+                  int planes, int64_t plane_stride, void* stream_) {
+  DFU_REQUIRE(C % 4 == 0 && C / 4 <= 32 * kLnMaxQuads, "layernorm: C=%d unsupported", C);
+  const int warps_per_block = 8;
+  const int blocks = (M + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<blocks, warps_per_block * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
+      x, M, C, gamma, beta, eps, static_cast<__half*>(out16), planes, plane_stride);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_cast_f16(const float* x, int B, int H, int W, int C, int mode, void* out16, int planes, int64_t plane_stride,
+                 void* stream_) {
+  DFU_REQUIRE(C % 4 == 0, "cast: C=%d", C);
+  DFU_REQUIRE(mode >= 0 && mode <= 2, "cast: mode");
+  DFU_REQUIRE(!(mode == 2 && ((H | W) & 1)), "cast: space-to-depth needs even H, W");
+  const long long total = static_cast<long long>(B) * H * W * (C / 4);
+  cast_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      x, B, H, W, C, mode, static_cast<__half*>(out16), planes, plane_stride);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+}

@@ -223,3 +223,112 @@ def conv(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, out_grid: Tupl
     set_epilogue(d, **epi)
     d.block_n, d.splits, d.stages = tune
     launch_gemm(d, ws)
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation / casts / small kernels
+# ---------------------------------------------------------------------------------------------
+def _new_operand(planes: int, shape, device) -> torch.Tensor:
+    return torch.empty((planes, *shape), dtype=torch.float16, device=device)
+
+
+def groupnorm(src0: torch.Tensor, gamma, beta, eps: float, silu: bool, prec: int, *, src1: Optional[torch.Tensor] = None,
+              out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None,
+              raw16: Optional[torch.Tensor] = None, groups: int = 32, ws: Optional[Workspace] = None):
+    """src0 [B,H,W,C0] (+ src1 [B,H,W,C1] concatenated on channels) fp32 NHWC.  out16/raw16: [planes,B,H,W,C]."""
+    B, H, W, C0 = src0.shape
+    C1 = 0 if src1 is None else src1.shape[-1]
+    L = lib()
+    need = L.dfu_groupnorm_workspace(B, H * W, C0 + C1, groups)
+    ws = ws or default_workspace()
+    buf = ws.ensure(need)
+    o = out16 if out16 is not None else raw16
+    planes = o.shape[0] if o is not None else 1
+    pstride = o.stride(0) if o is not None else 0
+    check(L.dfu_groupnorm(src0.data_ptr(), C0, _ptr(src1), C1, B, H * W, groups, gamma.data_ptr(), beta.data_ptr(),
+                          eps, int(silu), _ptr(out16), planes, pstride, _ptr(out32), _ptr(raw16), buf.data_ptr(),
+                          buf.numel(), _stream()), "dfu_groupnorm")
+
+
+def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: torch.Tensor):
+    """x [M, C] fp32 -> out16 [planes, M, C]."""
+    M, C = x.shape
+    check(lib().dfu_layernorm(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
+                              out16.shape[0], out16.stride(0), _stream()), "dfu_layernorm")
+
+
+CAST_PLAIN, CAST_UP2X, CAST_S2D = 0, 1, 2
+
+
+def cast_f16(x: torch.Tensor, mode: int, out16: torch.Tensor):
+    """x [B,H,W,C] fp32 NHWC -> out16 [planes, ...] (plain: B,H,W,C; up2x: B,2H,2W,C; s2d: 4*B,H/2,W/2,C)."""
+    B, H, W, Cc = x.shape
+    check(lib().dfu_cast_f16(x.data_ptr(), B, H, W, Cc, mode, out16.data_ptr(), out16.shape[0], out16.stride(0),
+                             _stream()), "dfu_cast_f16")
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float, out: torch.Tensor):
+    check(lib().dfu_timestep_embedding(t.data_ptr(), t.shape[0], dim, int(flip_sin_to_cos), float(freq_shift),
+                                       out.data_ptr(), _stream()), "dfu_timestep_embedding")
+
+
+def gemv(x: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, silu_in: bool = False, silu_out: bool = False):
+    B, K = x.shape
+    N = W.shape[0]
+    check(lib().dfu_gemv(x.data_ptr(), B, K, x.stride(0), W.data_ptr(), _ptr(bias), N, int(silu_in), int(silu_out),
+                         out.data_ptr(), out.stride(0), _stream()), "dfu_gemv")
+
+
+def conv_small_in(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias, out: torch.Tensor, batch: int,
+                  pre_scale: float = 1.0):
+    """srcs: up to 3 NCHW fp32 tensors ([B or 1, c, H, W]) gathered on channels; w [Cout, Cin, k, k]; out NHWC."""
+    H, W = srcs[0].shape[-2:]
+    a = []
+    for i in range(3):
+        if i < len(srcs):
+            s = srcs[i]
+            a += [s.data_ptr(), s.shape[1], 0 if s.shape[0] == 1 and batch > 1 else s.stride(0)]
+        else:
+            a += [None, 0, 0]
+    check(lib().dfu_conv_small_in(*a, batch, H, W, w.shape[-1], w.data_ptr(), _ptr(bias), w.shape[0], pre_scale,
+                                  out.data_ptr(), _stream()), "dfu_conv_small_in")
+
+
+def pack_small_out_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> fp32 [Cout, k*k, Cin]."""
+    O, I, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(O, kh * kw, I).contiguous()
+
+
+def conv_small_out(x: torch.Tensor, wp: torch.Tensor, bias, out: Optional[torch.Tensor], *, w2=None, b2=None,
+                   sample=None, prev=None, coef=None):
+    """x [B,H,W,Cin] fp32 NHWC; wp packed [Cout, k*k, Cin]; out NCHW.  Optional fused 1x1 (w2,b2) / scheduler step."""
+    B, H, W, Cin = x.shape
+    Cout, kk, _ = wp.shape
+    ksz = 3 if kk == 9 else 1
+    check(lib().dfu_conv_small_out(x.data_ptr(), B, H, W, Cin, ksz, wp.data_ptr(), _ptr(bias), Cout, _ptr(w2),
+                                   _ptr(b2), 0 if w2 is None else w2.shape[0], _ptr(out), _ptr(sample), _ptr(prev),
+                                   _ptr(coef), _stream()), "dfu_conv_small_out")
+
+
+def axpbypcz(x, e, n, a: float, b: float, c: float, y):
+    check(lib().dfu_axpbypcz(x.data_ptr(), e.data_ptr(), _ptr(n), a, b, c, y.data_ptr(), x.numel(), _stream()),
+          "dfu_axpbypcz")
+
+
+def gaussian_sample(moments: torch.Tensor, eps: Optional[torch.Tensor], scale: float, z: torch.Tensor):
+    B, C2, h, w = moments.shape
+    check(lib().dfu_gaussian_sample(moments.data_ptr(), _ptr(eps), B, C2 // 2, h * w, scale, z.data_ptr(), _stream()),
+          "dfu_gaussian_sample")
+
+
+def softmax_rows(s: torch.Tensor, scale: float, p16: torch.Tensor):
+    rows, n = s.shape
+    check(lib().dfu_softmax_rows(s.data_ptr(), rows, n, s.stride(0), scale, p16.data_ptr(), p16.stride(1),
+                                 p16.shape[0], p16.stride(0), _stream()), "dfu_softmax_rows")
+
+
+def transpose_f16(x16: torch.Tensor, out16: torch.Tensor):
+    planes, rows, cols = x16.shape
+    check(lib().dfu_transpose_f16(x16.data_ptr(), planes, rows, cols, x16.stride(0), out16.data_ptr(), out16.stride(0),
+                                  _stream()), "dfu_transpose_f16")

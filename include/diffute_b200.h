@@ -105,6 +105,60 @@ int dfu_gemm(const DfuGemm* desc, void* stream);
 /* Workspace bytes dfu_gemm needs for this descriptor with automatic tiling (0 if none). */
 size_t dfu_gemm_workspace(const DfuGemm* desc);
 
+/* ---- normalisation / operand casts (memory-bound, fp32 NHWC in, fp16 operand planes out) ------
+ * dfu_groupnorm: diffusers ResnetBlock2D.norm1/norm2 + SiLU, Transformer2DModel.norm, conv_norm_out, VAE
+ * group_norm (reached from app.ipynb:814/:793/:819).  The input may be the channel concat
+ * of two tensors (`torch.cat([h, skip], 1)` of the up blocks) which is never materialised in fp32.
+ * Writes any of: normalised(+SiLU) fp16 operand `out16`, the same in fp32 `out32` (feeds the few-channel
+ * fp32 output convs), and `raw16`, the un-normalised cast of the input (operand of the 1x1 conv_shortcut).
+ * workspace: dfu_groupnorm_workspace() bytes of per-chunk partial sums (deterministic two-stage reduction).
+ */
+size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups);
+int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, int groups,
+                  const float* gamma, const float* beta, float eps, int silu, void* out16, int planes,
+                  int64_t plane_stride, float* out32, void* raw16, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* BasicTransformerBlock.norm1/2/3 (LayerNorm, eps 1e-5) over [M, C] tokens -> fp16 operand planes. */
+int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* out16,
+                  int planes, int64_t plane_stride, void* stream);
+/* fp32 NHWC -> fp16 operand. mode 0: as is; 1: nearest 2x upsample (Upsample2D's F.interpolate folded into the
+ * operand of its conv); 2: space-to-depth parity planes [py*2+px][B][H/2][W/2][C] (Downsample2D stride-2 conv). */
+int dfu_cast_f16(const float* x, int B, int H, int W, int C, int mode, void* out16, int planes,
+                 int64_t plane_stride, void* stream);
+
+/* ---- small fp32 kernels ---------------------------------------------------------------------- */
+/* diffusers `Timesteps` (flip_sin_to_cos, freq_shift): t[B] fp32 -> [B, dim]. */
+int dfu_timestep_embedding(const float* t, int B, int dim, int flip_sin_to_cos, float freq_shift, float* out,
+                           void* stream);
+/* out[b,n] = act_out(bias[n] + sum_k W[n,k] * act_in(x[b,k])), B <= 16: TimestepEmbedding linear_1/linear_2 and all
+ * ResnetBlock2D.time_emb_proj layers (stacked into one W) in one launch each. */
+int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float* bias, int N, int silu_in,
+             int silu_out, float* out, int ldo, void* stream);
+/* Few-input-channel conv (UNet conv_in over the never-materialised cat([latents, mask, masked_latents]) of
+ * app.ipynb:811; VAE encoder conv_in; VAE post_quant_conv + decoder conv_in): NCHW fp32 sources -> NHWC fp32.
+ * bstrideN: elements between samples of source N (0 broadcasts). pre_scale multiplies the inputs (1/scaling_factor). */
+int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* src1, int c1, int64_t bstride1,
+                      const float* src2, int c2, int64_t bstride2, int B, int H, int W, int ksz, const float* w,
+                      const float* bias, int Cout, float pre_scale, float* out, void* stream);
+/* Few-output-channel conv (UNet conv_out, VAE conv_out + quant_conv): NHWC fp32 -> NCHW fp32, weights
+ * [Cout][k*k][Cin]; optional trailing 1x1 (w2,b2); optional fused scheduler update
+ * prev = coef[0]*sample + coef[1]*result  (DDIMScheduler.step collapsed, app.ipynb:816 / SURVEY a12). */
+int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, const float* w, const float* bias,
+                       int Cout, const float* w2, const float* b2, int Cout2, float* out, const float* sample,
+                       float* prev, const float* coef, void* stream);
+/* y = a*x + b*e (+ c*n): scheduler.step / add_noise / get_velocity in collapsed-coefficient form. */
+int dfu_axpbypcz(const float* x, const float* e, const float* n, float a, float b, float c, float* y,
+                 int64_t total, void* stream);
+/* DiagonalGaussianDistribution.sample()/mode() * scale from NCHW moments [B, 2*Cz, h, w] (eps NULL = mode). */
+int dfu_gaussian_sample(const float* moments, const float* eps, int B, int Cz, int HW, float scale, float* z,
+                        void* stream);
+/* Row softmax of fp32 scores*scale -> fp16 operand planes (single-head d=512 VAE attention). */
+int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void* p16, int ldp, int planes,
+                     int64_t plane_stride, void* stream);
+/* fp16 [planes][rows][cols] -> [planes][cols][rows]. */
+int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int64_t in_plane, void* out,
+                      int64_t out_plane, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
