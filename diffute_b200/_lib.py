@@ -91,6 +91,8 @@ SIGNATURES = {
     "dfu_axpbypcz": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64, _vp]),
     "dfu_gaussian_sample": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "dfu_softmax_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _i, _i, _i64, _vp]),
+    "dfu_attention": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _i, _i64,
+                           _vp]),
     "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp]),
 }
 

@@ -1,0 +1,322 @@
+// diffute_b200 — fused attention core for head dim 64 on tcgen05 (softmax(Q K^T * scale) V), sm_100a.
+//
+// Replaces diffusers' Attention core (attn1 self-attention over H*W tokens and attn2 cross-attention over the
+// 577 glyph tokens) in BasicTransformerBlock — SURVEY.md A.1, reached from app.ipynb:814.
+//
+// One CTA = 128 query rows of one (sample, head); it streams K/V in blocks of 128 keys:
+//   warps 0-3 : softmax warpgroup; thread r owns query row r (= TMEM lane r): row max / sum need no shuffles.
+//               S is read from TMEM with tcgen05.ld, P is written to shared memory as fp16 (hi [, lo]) in the
+//               128-byte-swizzled K-major layout the next MMA consumes; O is accumulated in registers with the
+//               online-softmax rescale.
+//   warp 4    : TMA producer (Q once; K and V double-buffered rings; 4-D maps so rows past the sequence end are
+//               zero-filled per sample and per plane).
+//   warp 5    : tcgen05.mma issuer: S = Q K^T (K-major B), then O_blk = P V with V consumed MN-major straight
+//               from its natural [key, d] layout (no transpose pass).
+// In FP16X2 mode both contractions run as three passes over (hi, lo) operand planes.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfu {
+
+constexpr int kAttnThreads = 192;
+constexpr int kBQ = 128;    // queries per CTA
+constexpr int kBKV = 128;   // keys per block
+constexpr int kD = 64;
+constexpr uint32_t kTile = 128 * 128;  // bytes of one [128 rows x 64 halfs] swizzled tile
+
+struct AttnParams {
+  int B, heads, Nq, Nk;
+  int planes;       // 1 or 2
+  float scale_log2; // softmax scale * log2(e)
+  int q_col0, k_col0, v_col0;  // column offsets of head 0 inside the Q / K / V matrices
+  __half* out;      // [planes][B*Nq][ldo], head h at columns h*64
+  int ldo;
+  long long out_plane_stride;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2];
+  __shared__ __align__(8) uint64_t s_full, s_free, p_full, o_full, o_free;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int planes = p.planes;
+  // layout: Q[planes] | K[2][planes] | V[2][planes] | P[planes][2 tiles]
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + planes * kTile;
+  uint8_t* sV = sK + 2 * planes * kTile;
+  uint8_t* sP = sV + 2 * planes * kTile;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nblk = (p.Nk + kBKV - 1) / kBKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(&s_full, 1);
+    mbar_init(&s_free, 128);
+    mbar_init(&p_full, 128);
+    mbar_init(&o_full, 1);
+    mbar_init(&o_free, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&tmem_base_smem, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_S = tmem_base;        // 128 columns
+  const uint32_t tmem_O = tmem_base + 128;  // 64 columns
+
+  if (warp == 4) {
+    // ===== TMA producer ======================================================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&q_full, planes * kTile);
+      for (int pl = 0; pl < planes; ++pl)
+        tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
+      for (int j = 0; j < nblk; ++j) {
+        const int slot = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1u;
+        mbar_wait(&k_empty[slot], par);
+        mbar_arrive_expect_tx(&k_full[slot], planes * kTile);
+        for (int pl = 0; pl < planes; ++pl)
+          tma_load_4d(sK + (slot * planes + pl) * kTile, &tmK, &k_full[slot], p.k_col0 + head * kD, j * kBKV, b, pl);
+        mbar_wait(&v_empty[slot], par);
+        mbar_arrive_expect_tx(&v_full[slot], planes * kTile);
+        for (int pl = 0; pl < planes; ++pl)
+          tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, j * kBKV, b, pl);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer ========================================================================
+    if (lane == 0) {
+      const uint32_t idesc_qk = umma_idesc_f16(128, kBKV, 0);
+      const uint32_t idesc_pv = umma_idesc_f16(128, kD, 1);  // B (= V) is MN-major
+      const int npass = planes == 2 ? 3 : 1;
+      auto issue_qk = [&](int j) {
+        const int slot = j & 1;
+        mbar_wait(&k_full[slot], (j >> 1) & 1);
+        if (j > 0) mbar_wait(&s_free, (j - 1) & 1);
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int ps = 0; ps < npass; ++ps) {
+          const int qa = (ps == 1) ? 1 : 0, kb = (ps == 2) ? 1 : 0;
+          const uint64_t ad = umma_desc_sw128(smem_u32(sQ + qa * kTile));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sK + (slot * planes + kb) * kTile));
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) {
+            umma_f16_ss(tmem_S, ad + 2 * k, bd + 2 * k, idesc_qk, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&s_full);
+        umma_commit(&k_empty[slot]);
+      };
+      mbar_wait(&q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_qk(j + 1);
+        const int slot = j & 1;
+        mbar_wait(&p_full, j & 1);
+        mbar_wait(&v_full[slot], (j >> 1) & 1);
+        if (j > 0) mbar_wait(&o_free, (j - 1) & 1);
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int ps = 0; ps < npass; ++ps) {
+          const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
+          const uint32_t pbase = smem_u32(sP + pa * 2 * kTile);
+          const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kTile);
+#pragma unroll
+          for (int k = 0; k < kBKV / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(pbase + (k >> 2) * kTile) + 2 * (k & 3);
+            const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
+            umma_f16_ss(tmem_O, ad, bd, idesc_pv, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&o_full);
+        umma_commit(&v_empty[slot]);
+      }
+    }
+  } else {
+    // ===== softmax warpgroup (warps 0..3) ======================================================
+    const int r = threadIdx.x;  // query row within the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    float acc[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
+    const float c2 = p.scale_log2;
+    const uint32_t prow = static_cast<uint32_t>(r) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+
+    auto accumulate_o = [&](int j) {
+      mbar_wait(&o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_O + lane_off + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
+      }
+      tc_fence_before();
+      mbar_arrive(&o_free);
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full, j & 1);
+      tc_fence_after();
+      const int kv_valid = p.Nk - j * kBKV;  // columns >= kv_valid are padding
+      // pass 1: row max
+      float mx = m;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float alpha = fast_exp2((m - mx) * c2);  // first block: exp2(-inf) = 0
+      // the previous block's P*V must be finished before P is overwritten; fold its result in now
+      if (j > 0) accumulate_o(j - 1);
+      // pass 2: probabilities -> shared memory (swizzled K-major fp16), row sum
+      const float mc = mx * c2;
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld_wait();
+        uint8_t* tile_hi = sP + (c >> 1) * kTile + prow;
+        uint8_t* tile_lo = sP + (2 + (c >> 1)) * kTile + prow;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // 16-byte units of 8 probabilities
+          __align__(16) __half h[8];
+          __align__(16) __half lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int col = c * 32 + u * 8 + i;
+            float pv = fast_exp2(__uint_as_float(raw[u * 8 + i]) * c2 - mc);
+            pv = (col < kv_valid) ? pv : 0.f;
+            rowsum += pv;
+            h[i] = __float2half_rn(pv);
+            lo[i] = __float2half_rn(pv - __half2float(h[i]));
+          }
+          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u);
+          const uint32_t off = (unit ^ sw) << 4;
+          *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
+          if (planes == 2) *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free);       // S may be overwritten by the next Q K^T
+      fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
+      mbar_arrive(&p_full);
+      l = l * alpha + rowsum;
+      m = mx;
+      alpha_prev = alpha;
+    }
+    accumulate_o(nblk - 1);
+    const int q = q0 + r;
+    if (q < p.Nq) {
+      const float inv = 1.0f / l;
+      __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        __align__(16) __half h[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = acc[u * 8 + i] * inv;
+          h[i] = __float2half_rn(v);
+          lo[i] = __float2half_rn(v - __half2float(h[i]));
+        }
+        *reinterpret_cast<uint4*>(dst + u * 8) = *reinterpret_cast<const uint4*>(h);
+        if (planes == 2) *reinterpret_cast<uint4*>(dst + p.out_plane_stride + u * 8) = *reinterpret_cast<const uint4*>(lo);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, int planes, long long plane_stride) {
+  uint64_t dims[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(N), static_cast<uint64_t>(B),
+                      static_cast<uint64_t>(planes)};
+  uint64_t str[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(N) * ld * 2,
+                     static_cast<uint64_t>(plane_stride) * 2};
+  uint32_t box[4] = {kD, 128, 1, 1};
+  return make_tmap_f16(m, base, 4, dims, str, box);
+}
+
+}  // namespace dfu
+
+using namespace dfu;
+
+extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, const void* k, int ldk,
+                             int k_col0, const void* v, int ldv, int v_col0, int64_t kv_plane_stride, int B, int heads,
+                             int Nq, int Nk, int planes, float scale, void* out, int ldo, int64_t out_plane_stride,
+                             void* stream_) {
+  DFU_REQUIRE(planes == 1 || planes == 2, "attention: planes=%d", planes);
+  DFU_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: empty problem");
+  DFU_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be x8");
+  DFU_REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "attention: column offsets must be x8");
+  CUtensorMap mQ, mK, mV;
+  int rc;
+  if ((rc = make_seq_map(&mQ, q, ldq, Nq, B, planes, q_plane_stride))) return rc;
+  if ((rc = make_seq_map(&mK, k, ldk, Nk, B, planes, kv_plane_stride))) return rc;
+  if ((rc = make_seq_map(&mV, v, ldv, Nk, B, planes, kv_plane_stride))) return rc;
+  AttnParams p;
+  p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.planes = planes;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.out = static_cast<__half*>(out);
+  p.ldo = ldo;
+  p.out_plane_stride = out_plane_stride;
+  const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr = true;
+  }
+  dim3 grid((Nq + kBQ - 1) / kBQ, heads, B);
+  attn_fwd_kernel<<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream_)>>>(mQ, mK, mV, p);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}

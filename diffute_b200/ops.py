@@ -332,3 +332,13 @@ def transpose_f16(x16: torch.Tensor, out16: torch.Tensor):
     planes, rows, cols = x16.shape
     check(lib().dfu_transpose_f16(x16.data_ptr(), planes, rows, cols, x16.stride(0), out16.data_ptr(), out16.stride(0),
                                   _stream()), "dfu_transpose_f16")
+
+
+def attention(q16: torch.Tensor, q_col0: int, k16: torch.Tensor, k_col0: int, v16: torch.Tensor, v_col0: int,
+              B: int, heads: int, Nq: int, Nk: int, scale: float, out16: torch.Tensor):
+    """q16 [planes, B*Nq, ldq], k16/v16 [planes, B*Nk, ld] fp16 operands (k16 and v16 share the plane stride);
+    out16 [planes, B*Nq, heads*64]."""
+    planes = q16.shape[0]
+    check(lib().dfu_attention(q16.data_ptr(), q16.stride(1), q_col0, q16.stride(0), k16.data_ptr(), k16.stride(1),
+                              k_col0, v16.data_ptr(), v16.stride(1), v_col0, k16.stride(0), B, heads, Nq, Nk, planes,
+                              scale, out16.data_ptr(), out16.stride(1), out16.stride(0), _stream()), "dfu_attention")

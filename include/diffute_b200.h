@@ -159,6 +159,17 @@ int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void
 int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int64_t in_plane, void* out,
                       int64_t out_plane, void* stream);
 
+/* ---- fused attention core (head dim 64) --------------------------------------------------------
+ * out[b, q, h*64:(h+1)*64] = softmax(Q_h K_h^T * scale) V_h for every sample b and head h: diffusers `Attention`
+ * core of BasicTransformerBlock.attn1 (self, Nk = Nq = H*W) and attn2 (cross, Nk = 577 glyph tokens), SURVEY A.1,
+ * reached from app.ipynb:814.  Q/K/V are fp16 operand matrices [planes][B*N][ld] with head h at columns
+ * col0 + 64*h (so a fused QKV projection output can be passed three times with different col0).  The result is
+ * written as an fp16 operand [planes][B*Nq][ldo] for the to_out projection.
+ */
+int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, const void* k, int ldk, int k_col0,
+                  const void* v, int ldv, int v_col0, int64_t kv_plane_stride, int B, int heads, int Nq, int Nk,
+                  int planes, float scale, void* out, int ldo, int64_t out_plane_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,55 @@
+"""GPU parity of the fused tcgen05 attention core against fp64 softmax attention on identical fp16 operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from diffute_b200 import ops as o
+    return o
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("B,heads,Nq,Nk,fused", [
+    (1, 5, 4096, 4096, True),     # level-0 self-attention
+    (2, 10, 1024, 1024, True),
+    (1, 20, 256, 256, True),
+    (3, 20, 64, 64, True),        # 8x8 level: fewer queries than the tile
+    (2, 5, 4096, 577, False),     # cross-attention over the glyph tokens (ragged key tail)
+    (1, 20, 64, 577, False),
+    (1, 2, 200, 130, False),      # ragged both ways
+])
+def test_attention(ops, planes, B, heads, Nq, Nk, fused):
+    C = heads * 64
+    scale = 0.125
+    if fused:
+        qkv = _rand((B * Nq, 3 * C), 1, 1.5)
+        qkv16 = ops.split_f16(qkv, planes)
+        q16 = k16 = v16 = qkv16
+        cols = (0, C, 2 * C)
+    else:
+        q16 = ops.split_f16(_rand((B * Nq, C), 2, 1.5), planes)
+        kv16 = ops.split_f16(_rand((B * Nk, 2 * C), 3, 1.5), planes)
+        k16 = v16 = kv16
+        cols = (0, 0, C)
+    out16 = torch.zeros((planes, B * Nq, C), dtype=torch.float16, device="cuda")
+    ops.attention(q16, cols[0], k16, cols[1], v16, cols[2], B, heads, Nq, Nk, scale, out16)
+    torch.cuda.synchronize()
+    qd = q16.double().sum(0)[:, cols[0]:cols[0] + C].reshape(B, Nq, heads, 64).permute(0, 2, 1, 3)
+    kd = k16.double().sum(0)[:, cols[1]:cols[1] + C].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
+    vd = v16.double().sum(0)[:, cols[2]:cols[2] + C].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
+    p = torch.softmax(qd @ kd.transpose(-1, -2) * scale, -1)
+    ref = (p @ vd).permute(0, 2, 1, 3).reshape(B * Nq, C)
+    got = out16.double().sum(0)
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    # planes=1: P and the output are rounded to fp16 (2^-11); planes=2: fp32-level (ex2.approx ~2^-22, lo*lo dropped)
+    assert err < (1.5e-3 if planes == 1 else 2e-5), err

@@ -1,0 +1,57 @@
+"""GPU parity of the whole UNet denoising step (diffusers call signature) against the fp32 CPU oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from diffute_b200 import arch, synthetic
+    from oracle import UNetOracle
+    sd = synthetic.make_state_dict(arch.unet_param_shapes())
+    orc = UNetOracle()
+    orc.load_state_dict(sd)
+    return sd, orc
+
+
+def _inputs(B, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    sample = torch.randn((B, 9, L, L), generator=g)
+    ehs = torch.randn((B, 577, 1024), generator=g)
+    return sample, ehs
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 4e-3), ("fp16x2", 2e-4)])
+@pytest.mark.parametrize("graph", [False, True])
+def test_unet_step_parity(setup, precision, tol, graph):
+    from diffute_b200.unet import UNet2DConditionModel
+    sd, orc = setup
+    unet = UNet2DConditionModel(sd, precision=precision, use_cuda_graph=graph)
+    for (B, L, t) in [(1, 32, 981), (2, 16, torch.tensor([500, 21]))]:
+        sample, ehs = _inputs(B, L, 7 + B)
+        ref = orc(sample, t, ehs).sample
+        for rep in range(2):  # second call exercises the cached context / graph replay
+            got = unet(sample.cuda(), t, ehs.cuda() if rep == 0 else ehs).sample.cpu()
+            err = ((got - ref).abs().max() / ref.abs().max()).item()
+            print(f"unet parity {precision} graph={graph} B={B} L={L} rep={rep}: maxrel {err:.3e}")
+            assert err < tol, err
+    # a 0-d tensor timestep and return_dict=False, as the reference passes them (app.ipynb:814)
+    sample, ehs = _inputs(1, 16, 3)
+    out = unet(sample.cuda(), torch.tensor(981), ehs.cuda(), return_dict=False)[0]
+    ref = orc(sample, torch.tensor(981), ehs).sample
+    assert ((out.cpu() - ref).abs().max() / ref.abs().max()).item() < tol
+
+
+def test_unet_rejects_bad_shapes(setup):
+    from diffute_b200.unet import UNet2DConditionModel
+    sd, _ = setup
+    unet = UNet2DConditionModel(sd, precision="fp16", use_cuda_graph=False)
+    with pytest.raises(ValueError):
+        unet(torch.zeros(1, 4, 16, 16).cuda(), 1, torch.zeros(1, 577, 1024).cuda())
+    with pytest.raises(ValueError):
+        unet(torch.zeros(1, 9, 12, 12).cuda(), 1, torch.zeros(1, 577, 1024).cuda())
+    with pytest.raises(ValueError):
+        unet(torch.zeros(1, 9, 16, 16).cuda(), 1, torch.zeros(1, 577, 768).cuda())
