@@ -85,15 +85,17 @@ SIGNATURES = {
     "dfu_cast_f16": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     "dfu_timestep_embedding": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "dfu_gemv": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
-    "dfu_conv_small_in": (_i, [_vp, _i, _i64, _vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp,
+    "dfu_conv_small_in": (_i, [_vp, _i, _i64, _vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp,
                                _vp]),
     "dfu_conv_small_out": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "dfu_axpbypcz": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64, _vp]),
+    "dfu_scheduler_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _i64, _vp]),
+    "dfu_axpby_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "dfu_gaussian_sample": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "dfu_softmax_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _i, _i, _i64, _vp]),
     "dfu_attention": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _i, _i64,
                            _vp]),
-    "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp]),
+    "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _i64, _vp]),
 }
 
 

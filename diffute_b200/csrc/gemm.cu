@@ -438,10 +438,10 @@ static int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& p
     *a_tx = static_cast<uint32_t>(pl.bw * pl.bh * pl.bn) * kBlockK * 2;
   }
   if (rc) return rc;
-  uint64_t bdims[2] = {static_cast<uint64_t>(o.b_ld), static_cast<uint64_t>(o.b_rows)};
+  uint64_t bdims[2] = {static_cast<uint64_t>(o.ntaps) * o.k_per_tap, static_cast<uint64_t>(o.b_rows)};
   uint64_t bstr[1] = {static_cast<uint64_t>(o.b_ld) * 2};
   uint32_t bbox[2] = {kBlockK, static_cast<uint32_t>(pl.block_n)};
-  DFU_REQUIRE(o.b_ld == o.ntaps * o.k_per_tap, "gemm: b_ld=%d != ntaps*k_per_tap", o.b_ld);
+  DFU_REQUIRE(o.b_ld >= o.ntaps * o.k_per_tap && o.b_ld % 8 == 0, "gemm: b_ld=%d < ntaps*k_per_tap", o.b_ld);
   return make_tmap_f16(mB, o.b, 2, bdims, bstr, bbox);
 }
 

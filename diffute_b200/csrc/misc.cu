@@ -85,6 +85,7 @@ struct SmallInSrc {
   const float* p[3];
   int c[3];
   long long bstride[3];  // elements between samples (0 broadcasts one sample to the batch)
+  int nhwc;              // 1: sources are NHWC [B,H,W,c] instead of NCHW
 };
 
 __global__ void __launch_bounds__(256)
@@ -111,7 +112,9 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
         int cc = c, si = 0;
         if (cc >= s.c[0]) { cc -= s.c[0]; si = 1; if (cc >= s.c[1]) { cc -= s.c[1]; si = 2; } }
-        v = s.p[si][b * s.bstride[si] + (static_cast<long long>(cc) * H + iy) * W + ix] * pre_scale;
+        const long long o = s.nhwc ? (static_cast<long long>(iy) * W + ix) * s.c[si] + cc
+                                   : (static_cast<long long>(cc) * H + iy) * W + ix;
+        v = s.p[si][b * s.bstride[si] + o] * pre_scale;
       }
     }
     sm[i] = v;
@@ -222,6 +225,35 @@ axpbypcz_kernel(const float* __restrict__ x, const float* __restrict__ e, const 
   }
 }
 
+// general scheduler update:  y = p0 * clamp?(a0*x + a1*m, -1, 1) + d0*x + d1*m + s*n
+// (DDIM / DDPM step for epsilon-, v- and sample-prediction with optional clip_sample)
+__global__ void __launch_bounds__(256)
+sched_step_kernel(const float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ n, float a0,
+                  float a1, float p0, float d0, float d1, float sn, int clip, float* __restrict__ y,
+                  float* __restrict__ x0_out, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float xv = x[i], mv = m[i];
+    float x0 = a0 * xv + a1 * mv;
+    if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float v = p0 * x0 + d0 * xv + d1 * mv;
+    if (n) v += sn * n[i];
+    y[i] = v;
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
+// y[b, i] = ca[b] * x[b, i] + cb[b] * e[b, i]   (add_noise / get_velocity with per-sample timesteps)
+__global__ void __launch_bounds__(256)
+axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ ca,
+                  const float* __restrict__ cb, float* __restrict__ y, long long per_row, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / per_row;
+    y[i] = ca[b] * x[i] + cb[b] * e[i];
+  }
+}
+
 // DiagonalGaussian sample from NCHW moments [B, 2*Cz, h, w]: z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps) * scale
 __global__ void __launch_bounds__(256)
 gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ eps, int B, int Cz, int HW,
@@ -280,7 +312,7 @@ softmax_rows_kernel(const float* __restrict__ s, int rows, int n, int lds, float
 }
 
 // fp16 [planes][rows][cols] -> transposed [planes][cols][rows] (V^T for the VAE attention's P*V GEMM)
-__global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, long long in_plane,
+__global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, int ld_in, long long in_plane,
                                      __half* __restrict__ out, long long out_plane) {
   __shared__ __half tile[32][33];
   const __half* src = in + blockIdx.z * in_plane;
@@ -288,7 +320,7 @@ __global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, in
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[j][threadIdx.x] = src[static_cast<size_t>(r) * cols + c];
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[static_cast<size_t>(r) * ld_in + c];
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -341,14 +373,15 @@ int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float*
 }
 
 int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* src1, int c1, int64_t bstride1,
-                      const float* src2, int c2, int64_t bstride2, int B, int H, int W, int ksz, const float* w,
-                      const float* bias, int Cout, float pre_scale, float* out, void* stream) {
+                      const float* src2, int c2, int64_t bstride2, int nhwc, int B, int H, int W, int ksz,
+                      const float* w, const float* bias, int Cout, float pre_scale, float* out, void* stream) {
   const int Cin = c0 + c1 + c2;
   DFU_REQUIRE(src0 && Cin > 0 && Cin <= 16 && (ksz == 1 || ksz == 3), "conv_small_in: Cin=%d ksz=%d", Cin, ksz);
   SmallInSrc s;
   s.p[0] = src0; s.p[1] = src1; s.p[2] = src2;
   s.c[0] = c0; s.c[1] = c1; s.c[2] = c2;
   s.bstride[0] = bstride0; s.bstride[1] = bstride1; s.bstride[2] = bstride2;
+  s.nhwc = nhwc;
   const long long npix = static_cast<long long>(B) * H * W;
   const int blocks = static_cast<int>((npix + 63) / 64);
   const size_t smem = 64ull * Cin * ksz * ksz * sizeof(float);
@@ -384,6 +417,23 @@ int dfu_axpbypcz(const float* x, const float* e, const float* n, float a, float 
   return DFU_OK;
 }
 
+int dfu_scheduler_step(const float* x, const float* m, const float* n, float a0, float a1, float p0, float d0,
+                       float d1, float sn, int clip, float* y, float* x0_out, int64_t total, void* stream) {
+  sched_step_kernel<<<ew_grid2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, m, n, a0, a1, p0, d0, d1,
+                                                                                        sn, clip, y, x0_out, total);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_axpby_rows(const float* x, const float* e, const float* ca, const float* cb, float* y, int B,
+                   int64_t per_row, void* stream) {
+  const long long total = static_cast<long long>(B) * per_row;
+  axpby_rows_kernel<<<ew_grid2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, e, ca, cb, y, per_row,
+                                                                                        total);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
 int dfu_gaussian_sample(const float* moments, const float* eps, int B, int Cz, int HW, float scale, float* z,
                         void* stream) {
   gaussian_sample_kernel<<<ew_grid2(static_cast<long long>(B) * Cz * HW, 256), 256, 0,
@@ -401,11 +451,11 @@ int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void
   return DFU_OK;
 }
 
-int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int64_t in_plane, void* out, int64_t out_plane,
-                      void* stream) {
+int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int ld_in, int64_t in_plane, void* out,
+                      int64_t out_plane, void* stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, planes), block(32, 8);
   transpose_f16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(in), rows, cols, in_plane, static_cast<__half*>(out), out_plane);
+      static_cast<const __half*>(in), rows, cols, ld_in, in_plane, static_cast<__half*>(out), out_plane);
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

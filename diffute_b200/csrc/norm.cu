@@ -27,16 +27,13 @@ __device__ __forceinline__ float4 gn_load(const GnSrc& s, int b, int pix, int cq
 }
 
 __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial) {
-  extern __shared__ float sm[];  // [2][C]
+  extern __shared__ float sm[];  // [TY][2][C] per-row-of-threads channel sums, reduced in a fixed order (deterministic)
   const int C = s.C0 + s.C1;
   const int cpg = C / groups;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, s.HW);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < 2 * C; i += nthr) sm[i] = 0.f;
-  __syncthreads();
   float sx[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
   for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
     const float4 v = gn_load(s, b, p, threadIdx.x);
@@ -46,19 +43,48 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
     sx[3] += v.w; sq[3] += v.w * v.w;
   }
   const int c = threadIdx.x * 4;
+  float* mine = sm + static_cast<size_t>(threadIdx.y) * 2 * C;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    atomicAdd(&sm[c + i], sx[i]);
-    atomicAdd(&sm[C + c + i], sq[i]);
+    mine[c + i] = sx[i];
+    mine[C + c + i] = sq[i];
   }
   __syncthreads();
   if (tid < groups) {
     float a = 0.f, q = 0.f;
-    for (int i = 0; i < cpg; ++i) {
-      a += sm[tid * cpg + i];
-      q += sm[C + tid * cpg + i];
+    for (int ty = 0; ty < static_cast<int>(blockDim.y); ++ty) {
+      const float* row = sm + static_cast<size_t>(ty) * 2 * C;
+      for (int i = 0; i < cpg; ++i) {
+        a += row[tid * cpg + i];
+        q += row[C + tid * cpg + i];
+      }
     }
     partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * groups + tid] = make_float2(a, q);
+  }
+}
+
+// per-(sample, group) mean / rstd from the chunk partials, combined in double in a fixed order (deterministic)
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int nchunks, int groups, double count, float eps,
+                                   float2* __restrict__ stats) {
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;  // 8 threads per group
+  if (g >= groups) return;
+  double sum = 0.0, sq = 0.0;
+  for (int k = sub; k < nchunks; k += 8) {
+    const float2 t = partial[(static_cast<size_t>(b) * nchunks + k) * groups + g];
+    sum += t.x;
+    sq += t.y;
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (sub == 0) {
+    const double mean = sum / count;
+    double var = sq / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[b * groups + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + eps)));
   }
 }
 
@@ -69,8 +95,7 @@ struct GnApply {
   GnSrc s;
   int groups;
   int pix_per_cta;
-  int nchunks;            // partial chunks per sample (gridDim.x of the stats launch)
-  const float2* partial;
+  const float2* stats;    // [B][groups] (mean, rstd)
   const float* gamma;
   const float* beta;
   float eps;
@@ -103,18 +128,9 @@ __global__ void gn_apply_kernel(GnApply a) {
   const int b = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   if (tid < a.groups) {
-    double sum = 0.0, sq = 0.0;
-    for (int k = 0; k < a.nchunks; ++k) {
-      const float2 t = a.partial[(static_cast<size_t>(b) * a.nchunks + k) * a.groups + tid];
-      sum += t.x;
-      sq += t.y;
-    }
-    const double n = static_cast<double>(cpg) * a.s.HW;
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[tid] = static_cast<float>(mean);
-    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+    const float2 t = a.stats[b * a.groups + tid];
+    s_mean[tid] = t.x;
+    s_rstd[tid] = t.y;
   }
   __syncthreads();
   const int c = threadIdx.x * 4;
@@ -252,7 +268,7 @@ size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups) {
   (void)C;
   const int ppc = HW >= 65536 ? 256 : (HW >= 4096 ? 64 : (HW >= 1024 ? 32 : 16));
   const int chunks = (HW + ppc - 1) / ppc;
-  return static_cast<size_t>(B) * chunks * groups * sizeof(float2);
+  return static_cast<size_t>(B) * (chunks + 1) * groups * sizeof(float2);
 }
 
 int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, int groups, const float* gamma,
@@ -277,14 +293,17 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   if (ty > ppc) ty = ppc;
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};
-  gn_stats_kernel<<<grid, block, 2 * C * sizeof(float), stream>>>(s, groups, ppc, static_cast<float2*>(workspace));
+  gn_stats_kernel<<<grid, block, static_cast<size_t>(ty) * 2 * C * sizeof(float), stream>>>(s, groups, ppc, static_cast<float2*>(workspace));
   DFU_CHECK_CUDA(cudaGetLastError());
   GnApply a;
   a.s = s;
   a.groups = groups;
   a.pix_per_cta = ppc;
-  a.nchunks = chunks;
-  a.partial = static_cast<const float2*>(workspace);
+  float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
+  gn_finalize_kernel<<<B, 8 * groups, 0, stream>>>(static_cast<const float2*>(workspace), chunks, groups,
+                                                   static_cast<double>(C / groups) * HW, eps, stats);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  a.stats = stats;
   a.gamma = gamma;
   a.beta = beta;
   a.eps = eps;

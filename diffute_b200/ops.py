@@ -122,17 +122,22 @@ def default_workspace() -> Workspace:
 
 
 def matrix_operand(op, a16: torch.Tensor, w16: torch.Tensor, K: int, planes: int):
-    """a16: fp16 [planes, M, K(ld)], w16: fp16 [planes*N, K]."""
-    rows = a16.shape[0] * a16.shape[1]
+    """a16: fp16 [planes, M, K] view (row stride a16.stride(1), plane stride a16.stride(0));
+    w16: fp16 [planes*N, K] packed weights, or a [planes, N, K] view of an activation used as the B operand."""
     op.a = a16.data_ptr()
     op.a_mode = 0
-    op.a_rows = rows
     op.a_ld = a16.stride(1)
-    op.a_plane = a16.shape[1]
+    op.a_plane = a16.stride(0) // a16.stride(1) if planes > 1 else a16.shape[1]
+    op.a_rows = op.a_plane * (planes - 1) + a16.shape[1]
     op.b = w16.data_ptr()
-    op.b_rows = w16.shape[0]
-    op.b_ld = w16.shape[1]
-    op.b_plane = w16.shape[0] // planes
+    if w16.dim() == 3:
+        op.b_ld = w16.stride(1)
+        op.b_plane = w16.stride(0) // w16.stride(1) if planes > 1 else w16.shape[1]
+        op.b_rows = op.b_plane * (planes - 1) + w16.shape[1]
+    else:
+        op.b_rows = w16.shape[0]
+        op.b_ld = w16.stride(0)
+        op.b_plane = w16.shape[0] // planes
     op.ntaps = 1
     op.k_per_tap = K
     _fill_taps(op, [(0, 0, 0)])
@@ -280,18 +285,22 @@ def gemv(x: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, silu_in: boo
 
 
 def conv_small_in(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias, out: torch.Tensor, batch: int,
-                  pre_scale: float = 1.0):
-    """srcs: up to 3 NCHW fp32 tensors ([B or 1, c, H, W]) gathered on channels; w [Cout, Cin, k, k]; out NHWC."""
-    H, W = srcs[0].shape[-2:]
+                  pre_scale: float = 1.0, nhwc: bool = False):
+    """srcs: up to 3 fp32 tensors gathered on channels, NCHW [B or 1, c, H, W] (or NHWC [B,H,W,c] with nhwc=True);
+    w [Cout, Cin, k, k]; out NHWC."""
+    if nhwc:
+        H, W = srcs[0].shape[1:3]
+    else:
+        H, W = srcs[0].shape[-2:]
     a = []
     for i in range(3):
         if i < len(srcs):
             s = srcs[i]
-            a += [s.data_ptr(), s.shape[1], 0 if s.shape[0] == 1 and batch > 1 else s.stride(0)]
+            a += [s.data_ptr(), s.shape[-1] if nhwc else s.shape[1], 0 if s.shape[0] == 1 and batch > 1 else s.stride(0)]
         else:
             a += [None, 0, 0]
-    check(lib().dfu_conv_small_in(*a, batch, H, W, w.shape[-1], w.data_ptr(), _ptr(bias), w.shape[0], pre_scale,
-                                  out.data_ptr(), _stream()), "dfu_conv_small_in")
+    check(lib().dfu_conv_small_in(*a, int(nhwc), batch, H, W, w.shape[-1], w.data_ptr(), _ptr(bias), w.shape[0],
+                                  pre_scale, out.data_ptr(), _stream()), "dfu_conv_small_in")
 
 
 def pack_small_out_weight(w: torch.Tensor) -> torch.Tensor:
@@ -329,9 +338,10 @@ def softmax_rows(s: torch.Tensor, scale: float, p16: torch.Tensor):
 
 
 def transpose_f16(x16: torch.Tensor, out16: torch.Tensor):
+    """x16 [planes, rows, cols] (row stride may exceed cols) -> out16 [planes, cols, rows] contiguous."""
     planes, rows, cols = x16.shape
-    check(lib().dfu_transpose_f16(x16.data_ptr(), planes, rows, cols, x16.stride(0), out16.data_ptr(), out16.stride(0),
-                                  _stream()), "dfu_transpose_f16")
+    check(lib().dfu_transpose_f16(x16.data_ptr(), planes, rows, cols, x16.stride(1), x16.stride(0), out16.data_ptr(),
+                                  out16.stride(0), _stream()), "dfu_transpose_f16")
 
 
 def attention(q16: torch.Tensor, q_col0: int, k16: torch.Tensor, k_col0: int, v16: torch.Tensor, v_col0: int,
@@ -342,3 +352,14 @@ def attention(q16: torch.Tensor, q_col0: int, k16: torch.Tensor, k_col0: int, v1
     check(lib().dfu_attention(q16.data_ptr(), q16.stride(1), q_col0, q16.stride(0), k16.data_ptr(), k16.stride(1),
                               k_col0, v16.data_ptr(), v16.stride(1), v_col0, k16.stride(0), B, heads, Nq, Nk, planes,
                               scale, out16.data_ptr(), out16.stride(1), out16.stride(0), _stream()), "dfu_attention")
+
+
+def scheduler_step(x, m, noise, a0, a1, p0, d0, d1, sn, clip: bool, y, x0_out=None):
+    check(lib().dfu_scheduler_step(x.data_ptr(), m.data_ptr(), _ptr(noise), a0, a1, p0, d0, d1, sn, int(clip),
+                                   y.data_ptr(), _ptr(x0_out), x.numel(), _stream()), "dfu_scheduler_step")
+
+
+def axpby_rows(x, e, ca, cb, y):
+    B = x.shape[0]
+    check(lib().dfu_axpby_rows(x.data_ptr(), e.data_ptr(), ca.data_ptr(), cb.data_ptr(), y.data_ptr(), B,
+                               x.numel() // B, _stream()), "dfu_axpby_rows")

@@ -56,7 +56,7 @@ typedef struct DfuGemmOperand {
   int32_t a_plane;      /* rows (mode 0) or images (mode 1) between the hi and lo planes */
   const void* b;        /* f16 weights, K-major: [b_rows, b_ld] */
   int32_t b_rows;       /* total rows incl. planes */
-  int32_t b_ld;         /* row stride in elements = total K of this group (ntaps * k_per_tap) */
+  int32_t b_ld;         /* row stride in elements (>= ntaps * k_per_tap, multiple of 8) */
   int32_t b_plane;      /* rows between the hi and lo planes */
   int32_t ntaps;        /* 1 (linear / 1x1) or 9 */
   int32_t k_per_tap;    /* contraction length per tap (multiple of 64) */
@@ -136,10 +136,11 @@ int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float*
              int silu_out, float* out, int ldo, void* stream);
 /* Few-input-channel conv (UNet conv_in over the never-materialised cat([latents, mask, masked_latents]) of
  * app.ipynb:811; VAE encoder conv_in; VAE post_quant_conv + decoder conv_in): NCHW fp32 sources -> NHWC fp32.
- * bstrideN: elements between samples of source N (0 broadcasts). pre_scale multiplies the inputs (1/scaling_factor). */
+ * bstrideN: elements between samples of source N (0 broadcasts). nhwc=1: sources are NHWC. pre_scale multiplies
+ * the inputs (1/scaling_factor). */
 int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* src1, int c1, int64_t bstride1,
-                      const float* src2, int c2, int64_t bstride2, int B, int H, int W, int ksz, const float* w,
-                      const float* bias, int Cout, float pre_scale, float* out, void* stream);
+                      const float* src2, int c2, int64_t bstride2, int nhwc, int B, int H, int W, int ksz,
+                      const float* w, const float* bias, int Cout, float pre_scale, float* out, void* stream);
 /* Few-output-channel conv (UNet conv_out, VAE conv_out + quant_conv): NHWC fp32 -> NCHW fp32, weights
  * [Cout][k*k][Cin]; optional trailing 1x1 (w2,b2); optional fused scheduler update
  * prev = coef[0]*sample + coef[1]*result  (DDIMScheduler.step collapsed, app.ipynb:816 / SURVEY a12). */
@@ -149,14 +150,21 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
 /* y = a*x + b*e (+ c*n): scheduler.step / add_noise / get_velocity in collapsed-coefficient form. */
 int dfu_axpbypcz(const float* x, const float* e, const float* n, float a, float b, float c, float* y,
                  int64_t total, void* stream);
+/* DDIMScheduler.step / DDPMScheduler.step (app.ipynb:816) in coefficient form, any prediction_type, optional
+ * clip_sample:  y = p0 * clamp?(a0*x + a1*m, -1, 1) + d0*x + d1*m + sn*n;  x0_out (optional) = the clamped x0. */
+int dfu_scheduler_step(const float* x, const float* m, const float* n, float a0, float a1, float p0, float d0,
+                       float d1, float sn, int clip, float* y, float* x0_out, int64_t total, void* stream);
+/* add_noise / get_velocity (train_diffute_v1.py:897, :907) with per-sample coefficients: y[b] = ca[b]*x[b] + cb[b]*e[b]. */
+int dfu_axpby_rows(const float* x, const float* e, const float* ca, const float* cb, float* y, int B,
+                   int64_t per_row, void* stream);
 /* DiagonalGaussianDistribution.sample()/mode() * scale from NCHW moments [B, 2*Cz, h, w] (eps NULL = mode). */
 int dfu_gaussian_sample(const float* moments, const float* eps, int B, int Cz, int HW, float scale, float* z,
                         void* stream);
 /* Row softmax of fp32 scores*scale -> fp16 operand planes (single-head d=512 VAE attention). */
 int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void* p16, int ldp, int planes,
                      int64_t plane_stride, void* stream);
-/* fp16 [planes][rows][cols] -> [planes][cols][rows]. */
-int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int64_t in_plane, void* out,
+/* fp16 [planes][rows][cols (row stride ld_in)] -> [planes][cols][rows]. */
+int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int ld_in, int64_t in_plane, void* out,
                       int64_t out_plane, void* stream);
 
 /* ---- fused attention core (head dim 64) --------------------------------------------------------
