@@ -103,11 +103,13 @@ class Workspace:
 
     def __init__(self, nbytes: int = 0, device="cuda"):
         self.device = device
+        self.generation = 0  # bumped on every reallocation: captured CUDA graphs holding the old address are stale
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
 
     def ensure(self, nbytes: int):
         if self.buf.numel() < nbytes:
             self.buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+            self.generation += 1
         return self.buf
 
 

@@ -1,0 +1,199 @@
+"""DiffUTEPipeline — the reference's `text_editing` sampling core (app.ipynb:772-819) as one call.
+
+The reference has no pipeline class; its loop is: TrOCR-encode the glyph image, VAE-encode the masked image,
+draw seeded noise, N x (cat -> unet -> scheduler.step), VAE-decode.  This class runs exactly that sequence on the
+native kernels, with the invariants hoisted: glyph K/V projections once per request, mask and masked-image latents
+gathered by conv_in instead of being concatenated each step, the scheduler update fused into conv_out, and the
+whole UNet step replayed as one CUDA graph.  The signature follows diffusers' StableDiffusionInpaintPipeline with
+`prompt_embeds` replaced by `glyph_embeds`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from .schedulers import DDIMScheduler, DDPMScheduler
+
+
+@dataclass
+class DiffUTEPipelineOutput:
+    images: object
+    latents: Optional[torch.Tensor] = None
+
+    def __getitem__(self, k):
+        if k in (0, "images"):
+            return self.images
+        raise KeyError(k)
+
+
+class DiffUTEPipeline:
+    def __init__(self, vae, unet, scheduler, glyph_encoder=None, glyph_processor=None):
+        self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.glyph_encoder, self.glyph_processor = glyph_encoder, glyph_processor
+        self.device = unet.device
+        self._graphs = {}
+
+    @classmethod
+    def from_pretrained(cls, path, unet_precision="fp16", vae_precision="fp16x2", scheduler_cls=DDIMScheduler, **kw):
+        """Folder layout of the reference: <path>/{unet,vae,scheduler}/ (app.ipynb:545-553)."""
+        from .unet import UNet2DConditionModel
+        from .vae import AutoencoderKL
+        unet = UNet2DConditionModel.from_pretrained(path, "unet", precision=unet_precision)
+        vae = AutoencoderKL.from_pretrained(path, "vae", precision=vae_precision)
+        return cls(vae, unet, scheduler_cls.from_pretrained(path, "scheduler"), **kw)
+
+    @classmethod
+    def from_synthetic(cls, unet_precision="fp16", vae_precision="fp16x2", seed: int = 1234, state_dicts=None):
+        from . import arch, synthetic
+        from .unet import UNet2DConditionModel
+        from .vae import AutoencoderKL
+        if state_dicts is None:
+            state_dicts = (synthetic.make_state_dict(arch.unet_param_shapes(), seed),
+                           synthetic.make_state_dict(arch.vae_param_shapes(), seed))
+        unet = UNet2DConditionModel(state_dicts[0], precision=unet_precision)
+        vae = AutoencoderKL(state_dicts[1], precision=vae_precision)
+        return cls(vae, unet, DDIMScheduler())
+
+    # ------------------------------------------------------------------------------------------
+    def encode_glyph(self, glyph_images):
+        """TrOCR encoder last_hidden_state [B,577,1024] (app.ipynb:773-776).  Runs stock transformers: the glyph
+        encoder is outside the hot path (once per request, ~1% of the FLOPs)."""
+        if self.glyph_encoder is None or self.glyph_processor is None:
+            raise ValueError("no glyph encoder attached: pass glyph_embeds [B,577,1024] instead of text/glyph images")
+        pv = self.glyph_processor(images=glyph_images, return_tensors="pt").pixel_values.to(self.device)
+        with torch.no_grad():
+            return self.glyph_encoder(pv).last_hidden_state.detach().float()
+
+    def _step_graph(self, B, h, w, fused: bool):
+        """Capture (once per shape) one denoising step: UNet + fused DDIM update, reading t / coefficients from the
+        device `state` row that the loop refreshes with one small copy per step."""
+        key = (B, h, w, fused)
+        g = self._graphs.get(key)
+        if g is not None and g[2] == self.unet.buffer_generation():
+            return g
+        A = self.unet.arena
+        lat = A.get("pipe.latents", (B, 4, h, w))
+        mask = A.get("pipe.mask", (B, 1, h, w))
+        ml = A.get("pipe.masked", (B, 4, h, w))
+        state = A.get("pipe.state", (B + 2,))
+        step_io = (lat, lat, state[B:B + 2]) if fused else None
+
+        def run():
+            return self.unet._forward_impl(B, h, w, step_io=step_io, srcs=[lat, mask, ml], t=state[:B])
+
+        run()  # warm-up: allocates static buffers
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            eps = run()
+        g = (graph, eps, self.unet.buffer_generation())
+        self._graphs[key] = g
+        return g
+
+    @torch.no_grad()
+    def __call__(self, image: Optional[torch.Tensor] = None, mask_image: Optional[torch.Tensor] = None,
+                 glyph_embeds: Optional[torch.Tensor] = None, text=None, masked_image: Optional[torch.Tensor] = None,
+                 height: Optional[int] = None, width: Optional[int] = None, num_inference_steps: int = 50,
+                 guidance_scale: float = 1.0, negative_glyph_embeds: Optional[torch.Tensor] = None, eta: float = 0.0,
+                 generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
+                 posterior_noise: Optional[torch.Tensor] = None, sample_posterior: bool = True,
+                 output_type: str = "pt", return_dict: bool = True):
+        """image / masked_image [B,3,H,W] in [-1,1]; mask_image [B,1,H,W] (1 = region to rewrite);
+        glyph_embeds [B,577,1024] (or `text` = glyph images for the attached TrOCR encoder).  Returns decoded RGB in
+        [-1,1] for output_type "pt" (what vae.decode returns at app.ipynb:819), [0,1] HWC numpy for "np", PIL for
+        "pil", the final latents for "latent"."""
+        if (glyph_embeds is None) == (text is None):
+            raise ValueError("pass exactly one of glyph_embeds / text")
+        if glyph_embeds is None:
+            glyph_embeds = self.encode_glyph(text)
+        if masked_image is None:
+            if image is None or mask_image is None:
+                raise ValueError("pass masked_image, or image and mask_image")
+            # the reference zeroes the masked pixels of the uint8 image before Normalize(0.5,0.5): they become -1
+            masked_image = torch.where(mask_image > 0.5, torch.full_like(image, -1.0), image)
+        if mask_image is None:
+            raise ValueError("mask_image is required")
+        dev = self.device
+        B, _, H, W = masked_image.shape
+        if (height and height != H) or (width and width != W):
+            raise ValueError("height/width must match the image tensors (resize is reference-side glue)")
+        vsf = 2 ** (len(self.vae.config["block_out_channels"]) - 1)
+        if H % (8 * vsf) or W % (8 * vsf):
+            raise ValueError(f"height and width must be multiples of {8 * vsf}")
+        h, w = H // vsf, W // vsf
+        sf = float(self.vae.config["scaling_factor"])
+        do_cfg = guidance_scale != 1.0 and negative_glyph_embeds is not None
+        sched = self.scheduler
+        fused = isinstance(sched, DDIMScheduler) and eta == 0.0 and not sched.config["clip_sample"] and not do_cfg
+        UB = 2 * B if do_cfg else B
+
+        # --- step-invariant work (once per request) -------------------------------------------------
+        post = self.vae.encode(masked_image.to(dev)).latent_dist                      # app.ipynb:793
+        if posterior_noise is not None:
+            ml = post.sample(noise=posterior_noise, scale=sf)
+        elif sample_posterior:
+            ml = post.sample(generator=generator, scale=sf)
+        else:
+            ml = post.mode(scale=sf)
+        mask_l = mask_image.to(dev, torch.float32)[:, :, ::vsf, ::vsf].contiguous()   # nearest, app.ipynb:787-790
+        if latents is None:                                                            # app.ipynb:796-801
+            gdev = generator.device if generator is not None else "cpu"
+            latents = torch.randn((B, 4, h, w), generator=generator, device=gdev, dtype=torch.float32)
+        latents = latents.to(dev, torch.float32) * float(sched.init_noise_sigma)
+        ctx = glyph_embeds.to(dev, torch.float32)
+        if do_cfg:
+            ctx = torch.cat([negative_glyph_embeds.to(dev, torch.float32), ctx], 0)
+        self.unet.prepare_context(ctx)
+        self.unet._ctx_key = None
+
+        A = self.unet.arena
+        graph, eps, _ = self._step_graph(UB, h, w, fused)
+        lat_buf = A.get("pipe.latents", (UB, 4, h, w))
+        A.get("pipe.mask", (UB, 1, h, w)).copy_(mask_l.repeat(2, 1, 1, 1) if do_cfg else mask_l)
+        A.get("pipe.masked", (UB, 4, h, w)).copy_(ml.repeat(2, 1, 1, 1) if do_cfg else ml)
+        state = A.get("pipe.state", (UB + 2,))
+        sched.set_timesteps(num_inference_steps)                                       # app.ipynb:803
+        ts = [int(t) for t in sched.timesteps]
+        rows = torch.zeros((len(ts), UB + 2), dtype=torch.float32)
+        for i, t in enumerate(ts):
+            rows[i, :UB] = float(t)
+            if fused:
+                rows[i, UB], rows[i, UB + 1] = sched.collapsed_coefficients(t)
+        rows = rows.to(dev)
+
+        # --- the loop (app.ipynb:806-816) -------------------------------------------------------------
+        if fused:
+            lat_buf.copy_(latents)
+            for i in range(len(ts)):
+                state.copy_(rows[i])       # one small D2D copy: timestep + DDIM coefficients of this step
+                graph.replay()             # UNet + scheduler update, latents advanced in place
+            latents = lat_buf
+        else:
+            eps_g = torch.empty((B, 4, h, w), device=dev) if do_cfg else None
+            for i, t in enumerate(ts):
+                lat_buf.copy_(torch.cat([latents, latents], 0) if do_cfg else latents)
+                state.copy_(rows[i])
+                graph.replay()
+                e = eps
+                if do_cfg:  # eps = eps_u + g (eps_c - eps_u)
+                    ops.axpbypcz(eps[:B], eps[B:], None, 1.0 - guidance_scale, guidance_scale, 0.0, eps_g)
+                    e = eps_g
+                if isinstance(sched, DDIMScheduler):
+                    latents = sched.step(e, t, latents, eta=eta, generator=generator, return_dict=False)[0]
+                else:
+                    latents = sched.step(e, t, latents, generator=generator, return_dict=False)[0]
+
+        if output_type == "latent":
+            out = latents.clone()
+            return DiffUTEPipelineOutput(out, out) if return_dict else (out,)
+        img = self.vae.decode(latents, pre_scale=1.0 / sf).sample                      # app.ipynb:818-819
+        if output_type in ("np", "pil"):
+            arr = (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).cpu().numpy()       # app.ipynb:822-824
+            if output_type == "pil":
+                from PIL import Image
+                arr = [Image.fromarray((a * 255).round().astype("uint8")) for a in arr]
+            img = arr
+        return DiffUTEPipelineOutput(img, latents) if return_dict else (img,)

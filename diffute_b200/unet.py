@@ -55,6 +55,7 @@ class Arena:
 
     def __init__(self, device):
         self.device = device
+        self.generation = 0  # bumped whenever a buffer is (re)allocated: graphs captured before are stale
         self.bufs: Dict[str, torch.Tensor] = {}
 
     def get(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
@@ -65,6 +66,7 @@ class Arena:
         if t is None or t.numel() < n or t.dtype != dtype:
             t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self.bufs[name] = t
+            self.generation += 1
         return t[:n].view(*shape)
 
     def nbytes(self) -> int:
@@ -349,11 +351,15 @@ class UNet2DConditionModel:
     # ------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------
-    def _forward_impl(self, B, H, W, step_io=None):
-        """All launches of one denoising step against the static buffers `in.sample`, `in.t` (and the context)."""
+    def _forward_impl(self, B, H, W, step_io=None, srcs=None, t=None):
+        """All launches of one denoising step against static buffers: `in.sample` [B,9,H,W] (or `srcs`, up to three
+        NCHW tensors whose channel concat is the UNet input — the cat of app.ipynb:811 is then never materialised),
+        `in.t` [B] and the prepared glyph context."""
         A, w, cfg, lay = self.arena, self.w, self.config, self.layout
-        sample = A.get("in.sample", (B, cfg["in_channels"], H, W))
-        t = A.get("in.t", (B,))
+        if srcs is None:
+            srcs = [A.get("in.sample", (B, cfg["in_channels"], H, W))]
+        if t is None:
+            t = A.get("in.t", (B,))
         c0 = cfg["block_out_channels"][0]
         # time embedding: sincos -> linear/SiLU -> linear, then all 22 time_emb_proj(SiLU(temb)) in one launch
         te = A.get("t.sincos", (B, c0))
@@ -366,7 +372,7 @@ class UNet2DConditionModel:
         ops.gemv(temb, w["temb_proj.w"], w["temb_proj.b"], tproj, silu_in=True)
 
         h = A.get("h.in", (B, H, W, c0))
-        ops.conv_small_in([sample], w["conv_in.w"], w["conv_in.b"], h, B)
+        ops.conv_small_in(srcs, w["conv_in.w"], w["conv_in.b"], h, B)
         skips = [h]
         n = 0
 
@@ -416,17 +422,20 @@ class UNet2DConditionModel:
         if not self.use_cuda_graph:
             return self._forward_impl(B, H, W)
         g = self._graphs.get(key)
-        if g is None:
+        if g is None or g[2] != self.buffer_generation():
             # warm-up run allocates every static buffer and sets function attributes; then capture
             self._forward_impl(B, H, W)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._forward_impl(B, H, W)
-            g = (graph, out)
+            g = (graph, out, self.buffer_generation())
             self._graphs[key] = g
         g[0].replay()
         return g[1]
+
+    def buffer_generation(self):
+        return (self.arena.generation, self.ws.generation)
 
     @torch.no_grad()
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None,
