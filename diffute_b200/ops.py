@@ -25,6 +25,32 @@ def npass_of(prec: int) -> int:
     return 3 if prec == PREC_FP16X2 else 1
 
 
+# ---------------------------------------------------------------------------------------------
+# launch accounting (bench.py reports `gpu_launches`) and optional per-kernel CUDA-event profiling
+# ---------------------------------------------------------------------------------------------
+STATS = {"launches": 0}
+PROFILE = None  # when a dict: kernel name -> list of (start_event, end_event, algorithmic_flops, algorithmic_bytes)
+
+
+class _Prof:
+    def __init__(self, name, launches=1, flops=0.0, nbytes=0.0):
+        self.name, self.launches, self.flops, self.nbytes = name, launches, flops, nbytes
+
+    def __enter__(self):
+        STATS["launches"] += self.launches
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.name, []).append((self.e0, self.e1, self.flops, self.nbytes))
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -170,7 +196,9 @@ def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
         buf = ws.ensure(need)
         d.workspace = buf.data_ptr()
         d.workspace_bytes = buf.numel()
-    check(L.dfu_gemm(C.byref(d), _stream()), "dfu_gemm")
+    k = sum(d.g[i].ntaps * d.g[i].k_per_tap for i in range(d.ngroups))
+    with _Prof("gemm_conv" if d.conv else "gemm_linear", 2 if need else 1, 2.0 * d.m * d.n * k):
+        check(L.dfu_gemm(C.byref(d), _stream()), "dfu_gemm")
 
 
 def set_epilogue(d: Gemm, *, out_f32=None, out_f16=None, bias=None, rowvec=None, rows_per_sample=0, residual=None,
@@ -252,16 +280,18 @@ def groupnorm(src0: torch.Tensor, gamma, beta, eps: float, silu: bool, prec: int
     o = out16 if out16 is not None else raw16
     planes = o.shape[0] if o is not None else 1
     pstride = o.stride(0) if o is not None else 0
-    check(L.dfu_groupnorm(src0.data_ptr(), C0, _ptr(src1), C1, B, H * W, groups, gamma.data_ptr(), beta.data_ptr(),
-                          eps, int(silu), _ptr(out16), planes, pstride, _ptr(out32), _ptr(raw16), buf.data_ptr(),
-                          buf.numel(), _stream()), "dfu_groupnorm")
+    with _Prof('groupnorm', 3, 0.0, float(B * H * W * (C0 + C1)) * (8 + 2 * planes * ((out16 is not None) + (raw16 is not None)) + 4 * (out32 is not None))):
+        check(L.dfu_groupnorm(src0.data_ptr(), C0, _ptr(src1), C1, B, H * W, groups, gamma.data_ptr(), beta.data_ptr(),
+                              eps, int(silu), _ptr(out16), planes, pstride, _ptr(out32), _ptr(raw16), buf.data_ptr(),
+                              buf.numel(), _stream()), "dfu_groupnorm")
 
 
 def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: torch.Tensor):
     """x [M, C] fp32 -> out16 [planes, M, C]."""
     M, C = x.shape
-    check(lib().dfu_layernorm(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
-                              out16.shape[0], out16.stride(0), _stream()), "dfu_layernorm")
+    with _Prof('layernorm', 1):
+        check(lib().dfu_layernorm(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
+                                  out16.shape[0], out16.stride(0), _stream()), "dfu_layernorm")
 
 
 CAST_PLAIN, CAST_UP2X, CAST_S2D = 0, 1, 2
@@ -270,20 +300,23 @@ CAST_PLAIN, CAST_UP2X, CAST_S2D = 0, 1, 2
 def cast_f16(x: torch.Tensor, mode: int, out16: torch.Tensor):
     """x [B,H,W,C] fp32 NHWC -> out16 [planes, ...] (plain: B,H,W,C; up2x: B,2H,2W,C; s2d: 4*B,H/2,W/2,C)."""
     B, H, W, Cc = x.shape
-    check(lib().dfu_cast_f16(x.data_ptr(), B, H, W, Cc, mode, out16.data_ptr(), out16.shape[0], out16.stride(0),
-                             _stream()), "dfu_cast_f16")
+    with _Prof('cast_f16', 1):
+        check(lib().dfu_cast_f16(x.data_ptr(), B, H, W, Cc, mode, out16.data_ptr(), out16.shape[0], out16.stride(0),
+                                 _stream()), "dfu_cast_f16")
 
 
 def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float, out: torch.Tensor):
-    check(lib().dfu_timestep_embedding(t.data_ptr(), t.shape[0], dim, int(flip_sin_to_cos), float(freq_shift),
-                                       out.data_ptr(), _stream()), "dfu_timestep_embedding")
+    with _Prof('timestep_embedding', 1):
+        check(lib().dfu_timestep_embedding(t.data_ptr(), t.shape[0], dim, int(flip_sin_to_cos), float(freq_shift),
+                                           out.data_ptr(), _stream()), "dfu_timestep_embedding")
 
 
 def gemv(x: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, silu_in: bool = False, silu_out: bool = False):
     B, K = x.shape
     N = W.shape[0]
-    check(lib().dfu_gemv(x.data_ptr(), B, K, x.stride(0), W.data_ptr(), _ptr(bias), N, int(silu_in), int(silu_out),
-                         out.data_ptr(), out.stride(0), _stream()), "dfu_gemv")
+    with _Prof('gemv', 1):
+        check(lib().dfu_gemv(x.data_ptr(), B, K, x.stride(0), W.data_ptr(), _ptr(bias), N, int(silu_in), int(silu_out),
+                             out.data_ptr(), out.stride(0), _stream()), "dfu_gemv")
 
 
 def conv_small_in(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias, out: torch.Tensor, batch: int,
@@ -301,8 +334,9 @@ def conv_small_in(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias, out: torc
             a += [s.data_ptr(), s.shape[-1] if nhwc else s.shape[1], 0 if s.shape[0] == 1 and batch > 1 else s.stride(0)]
         else:
             a += [None, 0, 0]
-    check(lib().dfu_conv_small_in(*a, int(nhwc), batch, H, W, w.shape[-1], w.data_ptr(), _ptr(bias), w.shape[0],
-                                  pre_scale, out.data_ptr(), _stream()), "dfu_conv_small_in")
+    with _Prof('conv_small_in', 1):
+        check(lib().dfu_conv_small_in(*a, int(nhwc), batch, H, W, w.shape[-1], w.data_ptr(), _ptr(bias), w.shape[0],
+                                      pre_scale, out.data_ptr(), _stream()), "dfu_conv_small_in")
 
 
 def pack_small_out_weight(w: torch.Tensor) -> torch.Tensor:
@@ -317,33 +351,38 @@ def conv_small_out(x: torch.Tensor, wp: torch.Tensor, bias, out: Optional[torch.
     B, H, W, Cin = x.shape
     Cout, kk, _ = wp.shape
     ksz = 3 if kk == 9 else 1
-    check(lib().dfu_conv_small_out(x.data_ptr(), B, H, W, Cin, ksz, wp.data_ptr(), _ptr(bias), Cout, _ptr(w2),
-                                   _ptr(b2), 0 if w2 is None else w2.shape[0], _ptr(out), _ptr(sample), _ptr(prev),
-                                   _ptr(coef), _stream()), "dfu_conv_small_out")
+    with _Prof('conv_small_out', 1):
+        check(lib().dfu_conv_small_out(x.data_ptr(), B, H, W, Cin, ksz, wp.data_ptr(), _ptr(bias), Cout, _ptr(w2),
+                                       _ptr(b2), 0 if w2 is None else w2.shape[0], _ptr(out), _ptr(sample), _ptr(prev),
+                                       _ptr(coef), _stream()), "dfu_conv_small_out")
 
 
 def axpbypcz(x, e, n, a: float, b: float, c: float, y):
-    check(lib().dfu_axpbypcz(x.data_ptr(), e.data_ptr(), _ptr(n), a, b, c, y.data_ptr(), x.numel(), _stream()),
-          "dfu_axpbypcz")
+    with _Prof('axpbypcz', 1):
+        check(lib().dfu_axpbypcz(x.data_ptr(), e.data_ptr(), _ptr(n), a, b, c, y.data_ptr(), x.numel(), _stream()),
+              "dfu_axpbypcz")
 
 
 def gaussian_sample(moments: torch.Tensor, eps: Optional[torch.Tensor], scale: float, z: torch.Tensor):
     B, C2, h, w = moments.shape
-    check(lib().dfu_gaussian_sample(moments.data_ptr(), _ptr(eps), B, C2 // 2, h * w, scale, z.data_ptr(), _stream()),
-          "dfu_gaussian_sample")
+    with _Prof('gaussian_sample', 1):
+        check(lib().dfu_gaussian_sample(moments.data_ptr(), _ptr(eps), B, C2 // 2, h * w, scale, z.data_ptr(), _stream()),
+              "dfu_gaussian_sample")
 
 
 def softmax_rows(s: torch.Tensor, scale: float, p16: torch.Tensor):
     rows, n = s.shape
-    check(lib().dfu_softmax_rows(s.data_ptr(), rows, n, s.stride(0), scale, p16.data_ptr(), p16.stride(1),
-                                 p16.shape[0], p16.stride(0), _stream()), "dfu_softmax_rows")
+    with _Prof('softmax_rows', 1):
+        check(lib().dfu_softmax_rows(s.data_ptr(), rows, n, s.stride(0), scale, p16.data_ptr(), p16.stride(1),
+                                     p16.shape[0], p16.stride(0), _stream()), "dfu_softmax_rows")
 
 
 def transpose_f16(x16: torch.Tensor, out16: torch.Tensor):
     """x16 [planes, rows, cols] (row stride may exceed cols) -> out16 [planes, cols, rows] contiguous."""
     planes, rows, cols = x16.shape
-    check(lib().dfu_transpose_f16(x16.data_ptr(), planes, rows, cols, x16.stride(1), x16.stride(0), out16.data_ptr(),
-                                  out16.stride(0), _stream()), "dfu_transpose_f16")
+    with _Prof('transpose_f16', 1):
+        check(lib().dfu_transpose_f16(x16.data_ptr(), planes, rows, cols, x16.stride(1), x16.stride(0), out16.data_ptr(),
+                                      out16.stride(0), _stream()), "dfu_transpose_f16")
 
 
 def attention(q16: torch.Tensor, q_col0: int, k16: torch.Tensor, k_col0: int, v16: torch.Tensor, v_col0: int,
@@ -351,17 +390,20 @@ def attention(q16: torch.Tensor, q_col0: int, k16: torch.Tensor, k_col0: int, v1
     """q16 [planes, B*Nq, ldq], k16/v16 [planes, B*Nk, ld] fp16 operands (k16 and v16 share the plane stride);
     out16 [planes, B*Nq, heads*64]."""
     planes = q16.shape[0]
-    check(lib().dfu_attention(q16.data_ptr(), q16.stride(1), q_col0, q16.stride(0), k16.data_ptr(), k16.stride(1),
-                              k_col0, v16.data_ptr(), v16.stride(1), v_col0, k16.stride(0), B, heads, Nq, Nk, planes,
-                              scale, out16.data_ptr(), out16.stride(1), out16.stride(0), _stream()), "dfu_attention")
+    with _Prof('attention', 1, 4.0 * B * heads * Nq * Nk * 64):
+        check(lib().dfu_attention(q16.data_ptr(), q16.stride(1), q_col0, q16.stride(0), k16.data_ptr(), k16.stride(1),
+                                  k_col0, v16.data_ptr(), v16.stride(1), v_col0, k16.stride(0), B, heads, Nq, Nk, planes,
+                                  scale, out16.data_ptr(), out16.stride(1), out16.stride(0), _stream()), "dfu_attention")
 
 
 def scheduler_step(x, m, noise, a0, a1, p0, d0, d1, sn, clip: bool, y, x0_out=None):
-    check(lib().dfu_scheduler_step(x.data_ptr(), m.data_ptr(), _ptr(noise), a0, a1, p0, d0, d1, sn, int(clip),
-                                   y.data_ptr(), _ptr(x0_out), x.numel(), _stream()), "dfu_scheduler_step")
+    with _Prof('scheduler_step', 1):
+        check(lib().dfu_scheduler_step(x.data_ptr(), m.data_ptr(), _ptr(noise), a0, a1, p0, d0, d1, sn, int(clip),
+                                       y.data_ptr(), _ptr(x0_out), x.numel(), _stream()), "dfu_scheduler_step")
 
 
 def axpby_rows(x, e, ca, cb, y):
     B = x.shape[0]
-    check(lib().dfu_axpby_rows(x.data_ptr(), e.data_ptr(), ca.data_ptr(), cb.data_ptr(), y.data_ptr(), B,
-                               x.numel() // B, _stream()), "dfu_axpby_rows")
+    with _Prof('axpby_rows', 1):
+        check(lib().dfu_axpby_rows(x.data_ptr(), e.data_ptr(), ca.data_ptr(), cb.data_ptr(), y.data_ptr(), B,
+                                   x.numel() // B, _stream()), "dfu_axpby_rows")

@@ -1,0 +1,196 @@
+"""CPU: host-side logic of the product — C-ABI surface, packing, tap tables, schedulers' coefficient math,
+checkpoint IO, sharding.  No kernel is launched here (no GPU in this container)."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from diffute_b200 import _lib
+    L = _lib.lib()  # builds with nvcc if needed; loads without a GPU
+    hdr = open(os.path.join(ROOT, "include", "diffute_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(dfu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    bound = set(_lib.SIGNATURES) | {"dfu_version", "dfu_last_error", "dfu_num_sms", "dfu_gemm", "dfu_gemm_workspace"}
+    assert set(names) == bound, set(names) ^ bound
+    assert L.dfu_version() >= 100
+
+
+def test_gemm_rejects_bad_descriptors_without_gpu():
+    import ctypes as C
+    from diffute_b200 import _lib
+    L = _lib.lib()
+    d = _lib.Gemm()
+    assert L.dfu_gemm(C.byref(d), None) == -1          # empty problem
+    assert b"empty" in L.dfu_last_error()
+    d.m, d.n, d.ngroups, d.npass = 128, 100, 1, 1        # n not a multiple of 32
+    assert L.dfu_gemm(C.byref(d), None) == -1
+    d.n, d.npass = 128, 2
+    assert L.dfu_gemm(C.byref(d), None) == -1
+    assert L.dfu_gemm(None, None) == -1
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors of DfuGemmOperand / DfuGemm have the layout a C compiler gives the header's structs."""
+    import ctypes as C
+    import subprocess
+    from diffute_b200 import _lib
+    src = tmp_path / "lay.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "diffute_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(DfuGemmOperand), sizeof(DfuGemm), '
+                   'offsetof(DfuGemmOperand,b), offsetof(DfuGemmOperand,tap_dn), offsetof(DfuGemm,g), '
+                   'offsetof(DfuGemm,conv), offsetof(DfuGemm,workspace));return 0;}')
+    exe = tmp_path / "lay"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(_lib.GemmOperand), C.sizeof(_lib.Gemm), _lib.GemmOperand.b.offset, _lib.GemmOperand.tap_dn.offset,
+            _lib.Gemm.g.offset, _lib.Gemm.conv.offset, _lib.Gemm.workspace.offset]
+    assert got == want, (got, want)
+
+
+def test_weight_packing_and_geglu_interleave():
+    from diffute_b200 import ops
+    w = torch.randn(8, 6, 3, 3)
+    p = ops.pack_conv_weight(w, 2)
+    assert p.shape == (16, 54) and p.dtype == torch.float16
+    rec = p.float().reshape(2, 8, 9, 6).sum(0)
+    assert torch.allclose(rec, w.permute(0, 2, 3, 1).reshape(8, 9, 6), atol=1e-6)
+    assert torch.equal(p[:8].float(), w.permute(0, 2, 3, 1).reshape(8, 54).half().float())
+    g = torch.arange(64.0)[:, None].repeat(1, 2)
+    gi = ops.geglu_interleave(g)
+    assert gi[:16, 0].tolist() == list(range(16)) and gi[16:32, 0].tolist() == list(range(32, 48))
+    assert gi[32:48, 0].tolist() == list(range(16, 32)) and gi[48:, 0].tolist() == list(range(48, 64))
+    x = torch.randn(1000) * 3
+    s = ops.split_f16(x, 2)
+    assert ((s.float().sum(0) - x).abs() <= 1e-6 * x.abs() + 1e-7).all()   # ~22-bit split; fp16 subnormal floor
+
+
+def test_stride2_tap_tables():
+    from diffute_b200 import ops
+    # UNet Downsample2D (pad 1): input row 2*yo + ky - 1
+    t = ops.taps_3x3_s2(3, 1)
+    for i, (dn, dy, dx) in enumerate(t):
+        ky, kx = divmod(i, 3)
+        py, px = dn // 3 // 2, dn // 3 % 2
+        for yo in (0, 5):
+            assert 2 * (yo + dy) + py == 2 * yo + ky - 1
+            assert 2 * (yo + dx) + px == 2 * yo + kx - 1
+    # VAE encoder (pad (0,1,0,1)): input row 2*yo + ky
+    for i, (dn, dy, dx) in enumerate(ops.taps_3x3_s2(1, 0)):
+        ky, kx = divmod(i, 3)
+        assert 2 * dy + dn // 2 == ky and 2 * dx + dn % 2 == kx
+    assert ops.taps_3x3_s1()[0] == (0, -1, -1) and ops.taps_3x3_s1()[8] == (0, 1, 1)
+
+
+def test_scheduler_tables_and_coefficients_match_oracle():
+    from diffute_b200.schedulers import DDIMScheduler, DDPMScheduler
+    from oracle.schedulers import DDIMOracle, DDPMOracle
+    s, o = DDIMScheduler(), DDIMOracle()
+    assert torch.equal(s.alphas_cumprod, o.alphas_cumprod)
+    s.set_timesteps(50)
+    o.set_timesteps(50)
+    assert s.timesteps.tolist() == o.timesteps.tolist() == list(range(981, 0, -20))
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))["ddim_sd2_coeffs"]
+    for t, (gx, ge) in zip(s.timesteps.tolist(), gold):
+        cx, ce = s.collapsed_coefficients(t)
+        ox, oe = o.collapsed_coeffs(t)
+        assert abs(cx - ox) < 1e-12 and abs(ce - oe) < 1e-12
+        assert abs(cx - gx) < 1e-12 and abs(ce - ge) < 1e-12
+    # general coefficient form reproduces the oracle's step (CPU arithmetic only) incl. clip / v-prediction / eta
+    for cfg in (dict(), dict(prediction_type="v_prediction"), dict(clip_sample=True), dict(prediction_type="sample")):
+        s, o = DDIMScheduler(**cfg), DDIMOracle(**cfg)
+        s.set_timesteps(20)
+        o.set_timesteps(20)
+        x, m, n = torch.randn(2, 4, 8, 8).double(), torch.randn(2, 4, 8, 8).double(), torch.randn(2, 4, 8, 8).double()
+        o.alphas_cumprod = o.alphas_cumprod.double()
+        o.final_alpha_cumprod = o.final_alpha_cumprod.double()
+        for t in (951, 501, 1):
+            for eta in (0.0, 0.7):
+                a0, a1, p0, d0, d1, sg, clip = s.step_coefficients(t, eta)
+                x0 = a0 * x + a1 * m
+                if clip:
+                    x0 = x0.clamp(-1, 1)
+                got = p0 * x0 + d0 * x + d1 * m + sg * n
+                ref = o.step(m, t, x, eta=eta, variance_noise=n).prev_sample
+                assert torch.allclose(got, ref, atol=1e-9), (cfg, t, eta)
+    s, o = DDPMScheduler(), DDPMOracle()
+    s.set_timesteps(50)
+    o.set_timesteps(50)
+    o.alphas_cumprod = o.alphas_cumprod.double()
+    x, m, n = torch.randn(2, 4, 8, 8).double(), torch.randn(2, 4, 8, 8).double(), torch.randn(2, 4, 8, 8).double()
+    for t in (980, 500, 0):
+        a0, a1, p0, d0, d1, sg, clip = s.step_coefficients(t)
+        got = p0 * (a0 * x + a1 * m) + d0 * x + d1 * m + sg * n
+        ref = o.step(m, t, x, noise=n).prev_sample
+        assert torch.allclose(got, ref, atol=1e-9)
+    with pytest.raises(ValueError):
+        DDIMScheduler().step_coefficients(981)       # set_timesteps not called
+    with pytest.raises(ValueError):
+        DDIMScheduler().set_timesteps(2000)
+
+
+def test_scheduler_from_pretrained_pndm_style_config(tmp_path):
+    """The SD2-inpainting scheduler folder holds a PNDM config that DDIM/DDPM reinterpret."""
+    from diffute_b200.schedulers import DDIMScheduler, DDPMScheduler
+    os.makedirs(tmp_path / "scheduler")
+    cfg = {"_class_name": "PNDMScheduler", "_diffusers_version": "0.8.0", "beta_end": 0.012,
+           "beta_schedule": "scaled_linear", "beta_start": 0.00085, "num_train_timesteps": 1000,
+           "set_alpha_to_one": False, "skip_prk_steps": True, "steps_offset": 1, "trained_betas": None,
+           "clip_sample": False, "prediction_type": "epsilon"}
+    json.dump(cfg, open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    s = DDIMScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
+    assert s.config.steps_offset == 1 and s.config["prediction_type"] == "epsilon" and s.init_noise_sigma == 1.0
+    d = DDPMScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
+    assert d.num_train_timesteps == 1000 and len(d) == 1000
+
+
+def test_checkpoint_roundtrip_and_legacy_vae_keys(tmp_path):
+    from diffute_b200 import checkpoint
+    sd = {"encoder.mid_block.attentions.0.query.weight": torch.randn(4, 4),
+          "encoder.mid_block.attentions.0.proj_attn.bias": torch.randn(4),
+          "decoder.conv_in.weight": torch.randn(2, 2, 3, 3)}
+    for safe in (True, False):
+        checkpoint.save_diffusers_folder(str(tmp_path / f"m{safe}"), "vae", {"scaling_factor": 0.18215}, sd,
+                                         "AutoencoderKL", safe_serialization=safe)
+        cfg, back = checkpoint.load_diffusers_folder(str(tmp_path / f"m{safe}"), "vae")
+        assert cfg["scaling_factor"] == 0.18215 and cfg["_class_name"] == "AutoencoderKL"
+        assert all(torch.equal(back[k], sd[k]) for k in sd)
+    r = checkpoint.remap_legacy_vae_keys(sd)
+    assert "encoder.mid_block.attentions.0.to_q.weight" in r
+    assert "encoder.mid_block.attentions.0.to_out.0.bias" in r and "decoder.conv_in.weight" in r
+    with pytest.raises(FileNotFoundError):
+        checkpoint.load_diffusers_folder(str(tmp_path / "nope"), "unet")
+
+
+def test_synthetic_is_deterministic_and_order_independent():
+    from diffute_b200 import arch, synthetic
+    shapes = arch.vae_param_shapes()
+    a = synthetic.make_state_dict(shapes)
+    b = synthetic.make_state_dict(dict(reversed(list(shapes.items()))))
+    assert all(torch.equal(a[k], b[k]) for k in shapes)
+    i1, i2 = synthetic.make_inputs(2, 64, 64), synthetic.make_inputs(2, 64, 64)
+    assert all(torch.equal(i1[k], i2[k]) for k in i1)
+    m = i1["mask"]
+    assert m[0, 0, 16:32, 8:56].min() == 1 and m.sum() == 2 * 16 * 48
+    assert (i1["masked_image"][m.expand(-1, 3, -1, -1) > 0.5] == -1).all()
+
+
+def test_engine_fails_loudly_without_cuda():
+    """No CPU fallback: constructing the engine / launching a kernel without a GPU must raise, not degrade."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only box")
+    from diffute_b200 import arch, synthetic
+    from diffute_b200.vae import AutoencoderKL
+    with pytest.raises(Exception):
+        AutoencoderKL(synthetic.make_state_dict(arch.vae_param_shapes()), device="cuda")
+    assert "oracle" not in "".join(open(os.path.join(ROOT, "diffute_b200", f)).read()
+                                   for f in os.listdir(os.path.join(ROOT, "diffute_b200"))
+                                   if f.endswith(".py")).replace("the oracle", "").replace("CPU oracle", "")
