@@ -1,0 +1,36 @@
+"""Full-size parity on the GPU box: 512x512, 50 DDIM steps, decoded RGB vs the fp32 CPU oracle (BASELINE bar 1e-3).
+Writes gpurun_out/parity_512.json.  Usage: python scripts/parity_512.py [px] [steps] [modes...]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from diffute_b200 import arch, synthetic
+from diffute_b200.pipeline import DiffUTEPipeline
+from oracle import DDIMOracle, UNetOracle, VAEOracle, sample_loop
+
+px = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+modes = sys.argv[3:] or ["mixed", "fp16x2"]
+torch.set_num_threads(os.cpu_count())
+usd = synthetic.make_state_dict(arch.unet_param_shapes())
+vsd = synthetic.make_state_dict(arch.vae_param_shapes())
+inp = synthetic.make_inputs(1, px, px)
+uo, vo = UNetOracle(), VAEOracle()
+uo.load_state_dict(usd); vo.load_state_dict(vsd)
+t0 = time.time()
+ref = sample_loop(uo, vo, DDIMOracle(), inp["masked_image"], inp["mask"], inp["glyph_embeds"], inp["latents"], steps,
+                  posterior_noise=inp["posterior_noise"])
+t_cpu = time.time() - t0
+res = {"px": px, "steps": steps, "cpu_oracle_seconds": t_cpu, "cpu_cores": os.cpu_count(), "modes": {}}
+for m in modes:
+    up, vp = {"mixed": ("fp16", "fp16x2"), "fp16x2": ("fp16x2", "fp16x2"), "fp16": ("fp16", "fp16")}[m]
+    pipe = DiffUTEPipeline.from_synthetic(up, vp, state_dicts=(usd, vsd))
+    out = pipe(masked_image=inp["masked_image"], mask_image=inp["mask"], glyph_embeds=inp["glyph_embeds"],
+               latents=inp["latents"], posterior_noise=inp["posterior_noise"], num_inference_steps=steps).images.cpu()
+    err = ((out - ref).abs().max() / ref.abs().max()).item()
+    res["modes"][m] = {"rgb_max_rel_err": err, "passes_1e-3": err <= 1e-3}
+    print(m, err, flush=True)
+    del pipe
+    torch.cuda.empty_cache()
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/parity_512.json", "w"), indent=1)
+print(json.dumps(res))
