@@ -34,6 +34,12 @@ VAE_DEC_GFLOP = 2514.52
 IMAGE_GFLOP = NSTEPS * (UNET_GFLOP - UNET_CTX_GFLOP) + UNET_CTX_GFLOP + VAE_ENC_GFLOP + VAE_DEC_GFLOP
 
 
+def _cpu_threads() -> int:
+    """Threads for the CPU arm: the oracle's torch/oneDNN kernels stop scaling (and regress badly) far below the 128
+    hardware threads of the GPU box's host — 64 s per UNet step with 128 threads vs ~3 s with 8-32 — so cap at 32."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("DFU_CPU_THREADS", "32"))))
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -98,7 +104,7 @@ def cpu_reference_sample(threads=None, unet_reps=1):
     import torch
     from diffute_b200 import arch, synthetic
     from oracle import UNetOracle, VAEOracle
-    threads = threads or os.cpu_count()
+    threads = threads or _cpu_threads()
     torch.set_num_threads(threads)
     u, v = UNetOracle(), VAEOracle()
     u.load_state_dict(synthetic.make_state_dict(arch.unet_param_shapes()))
@@ -127,7 +133,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     import torch
-    threads = os.cpu_count()
+    threads = _cpu_threads()
     from diffute_b200 import arch, synthetic
     from oracle import UNetOracle, VAEOracle
     torch.set_num_threads(threads)

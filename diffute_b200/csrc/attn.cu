@@ -43,6 +43,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2];
   __shared__ __align__(8) uint64_t s_full, s_free, p_full, o_full, o_free;
@@ -92,6 +93,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_S = tmem_base;        // 128 columns
   const uint32_t tmem_O = tmem_base + 128;  // 64 columns
+  pdl_wait();
 
   if (warp == 4) {
     // ===== TMA producer ======================================================================
@@ -316,7 +318,7 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
     attr = true;
   }
   dim3 grid((Nq + kBQ - 1) / kBQ, heads, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream_)>>>(mQ, mK, mV, p);
+  DFU_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream_), mQ, mK, mV, p));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -81,6 +81,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel lets its successor start launching at once (its CTAs only fill
+// SM slots the running grid no longer needs) and waits for its predecessor right before touching global memory,
+// so launch latency and the barrier/TMEM prologue overlap the previous kernel's tail.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // proxies / fences
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> async proxy (UMMA/TMA)

@@ -57,70 +57,65 @@ struct GemmKernelParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// shared epilogue: 32 consecutive columns [n, n+32) of output row m
+// shared epilogue, one 4-column quad of output row m at a time so that consecutive lanes touch consecutive 16-byte
+// pieces of a row (coalesced residual loads and output stores).
+//   v = alpha*acc + bias[n] + rowvec[sample(m), n] + residual[m, n]  ->  fp32 | fp16 hi/lo planes
+//   GEGLU: out[m, n/2] = (a + bias_a) * gelu_erf(g + bias_g), a/g = value / gate quads 16 columns apart
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_f16x8(__half* dst, const float* v, bool lo_plane, __half* dst_lo) {
-  __align__(16) __half h[8];
-  __align__(16) __half l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __float2half_rn(v[i]);
-    l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+__device__ __forceinline__ void store_f16x4(__half* dst, float4 v, bool lo_plane, long long plane_stride) {
+  __align__(8) __half h[4];
+  h[0] = __float2half_rn(v.x); h[1] = __float2half_rn(v.y); h[2] = __float2half_rn(v.z); h[3] = __float2half_rn(v.w);
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+  if (lo_plane) {
+    __align__(8) __half l[4];
+    l[0] = __float2half_rn(v.x - __half2float(h[0]));
+    l[1] = __float2half_rn(v.y - __half2float(h[1]));
+    l[2] = __float2half_rn(v.z - __half2float(h[2]));
+    l[3] = __float2half_rn(v.w - __half2float(h[3]));
+    *reinterpret_cast<uint2*>(dst + plane_stride) = *reinterpret_cast<const uint2*>(l);
   }
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
-  if (lo_plane) *reinterpret_cast<uint4*>(dst_lo) = *reinterpret_cast<const uint4*>(l);
 }
 
-__device__ __forceinline__ void epilogue_chunk32(const EpiParams& e, int m, int n, float (&v)[32]) {
-  if (e.alpha != 1.0f) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= e.alpha;
-  }
+__device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, float4 v) {
+  v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
   if (e.bias) {
-    const float4* b = reinterpret_cast<const float4*>(e.bias + n);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = __ldg(b + i);
-      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
+    const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
   if (e.rowvec) {
-    const float4* b =
-        reinterpret_cast<const float4*>(e.rowvec + static_cast<size_t>(m / e.rows_per_sample) * e.rowvec_ld + n);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = __ldg(b + i);
-      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
+    const float4 t = __ldg(reinterpret_cast<const float4*>(
+        e.rowvec + static_cast<size_t>(m / e.rows_per_sample) * e.rowvec_ld + n));
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
-  if (e.epi == DFU_EPI_GEGLU) {
-    float o[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = v[i] * gelu_erf_f(v[16 + i]);
-    __half* dst = e.out_f16 + static_cast<size_t>(m) * e.ldh + (n >> 1);
-    store_f16x8(dst, o, e.out_planes > 1, dst + e.out_plane_stride);
-    store_f16x8(dst + 8, o + 8, e.out_planes > 1, dst + e.out_plane_stride + 8);
-    return;
-  }
+  return v;
+}
+
+__device__ __forceinline__ void epi_quad(const EpiParams& e, int m, int n, float4 v) {
+  v = epi_affine(e, m, n, v);
   if (e.residual) {
-    const float4* r = reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(m) * e.ldr + n);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = r[i];
-      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
+    const float4 t = *reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(m) * e.ldr + n);
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
   if (e.epi == DFU_EPI_F32) {
-    float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;
   } else {
-    __half* dst = e.out_f16 + static_cast<size_t>(m) * e.ldh + n;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      store_f16x8(dst + 8 * i, v + 8 * i, e.out_planes > 1, dst + e.out_plane_stride + 8 * i);
+    store_f16x4(e.out_f16 + static_cast<size_t>(m) * e.ldh + n, v, e.out_planes > 1, e.out_plane_stride);
   }
 }
+
+// n_a = packed column of the value quad (the gate quad sits at n_a + 16); output column = block*16 + offset
+__device__ __forceinline__ void epi_geglu_quad(const EpiParams& e, int m, int n_a, float4 a, float4 g) {
+  a = epi_affine(e, m, n_a, a);
+  g = epi_affine(e, m, n_a + 16, g);
+  float4 o;
+  o.x = a.x * gelu_erf_f(g.x); o.y = a.y * gelu_erf_f(g.y); o.z = a.z * gelu_erf_f(g.z); o.w = a.w * gelu_erf_f(g.w);
+  const int n_out = (n_a >> 5) * 16 + (n_a & 15);
+  store_f16x4(e.out_f16 + static_cast<size_t>(m) * e.ldh + n_out, o, e.out_planes > 1, e.out_plane_stride);
+}
+
+constexpr int kStageLd = 36;                          // floats per staged row (16-byte aligned, conflict-free)
+constexpr int kStageFloats = 32 * kStageLd;           // per epilogue warp
+constexpr uint32_t kStageBytes = 4 * kStageFloats * 4;
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -129,6 +124,7 @@ __global__ void __launch_bounds__(kGemmThreads)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ GemmKernelParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -182,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
@@ -269,21 +266,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // TMEM gives each thread one output row; a per-warp smem transpose turns that into row-contiguous 16-byte
+    // quads per lane so global traffic is coalesced (4 full 128-byte lines per warp instruction).
+    // (the operand ring is idle once tmem_full has fired, so its first 18 KiB double as the staging area)
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * kStageFloats;
+    const int vmask = valid ? 1 : 0;
     for (int c = 0; c < p.block_n; c += 32) {
       uint32_t raw[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
       tmem_ld_wait();
-      if (valid) {
-        float v[32];
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const int n = n_tile0 + c;
-        if (p.splits > 1) {
-          float4* o = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + m) * p.e.N + n);
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * i) =
+            make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
+                        __uint_as_float(raw[4 * i + 3]));
+      __syncwarp();
+      const int n = n_tile0 + c;
+      if (p.splits == 1 && p.e.epi == DFU_EPI_GEGLU) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          epilogue_chunk32(p.e, m, n, v);
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + (lane >> 2), cq = lane & 3;
+          const int mr = __shfl_sync(0xffffffffu, m, row);
+          const int vr = __shfl_sync(0xffffffffu, vmask, row);
+          const float4 a = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
+          const float4 g = *reinterpret_cast<const float4*>(stage + row * kStageLd + 16 + cq * 4);
+          if (vr) epi_geglu_quad(p.e, mr, n + cq * 4, a, g);
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), cq = lane & 7;
+          const int mr = __shfl_sync(0xffffffffu, m, row);
+          const int vr = __shfl_sync(0xffffffffu, vmask, row);
+          const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
+          if (vr) {
+            if (p.splits > 1)
+              *reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mr) * p.e.N + n + cq * 4) = v;
+            else
+              epi_quad(p.e, mr, n + cq * 4, v);
+          }
         }
       }
     }
@@ -297,26 +319,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 }
 
-// split-K: sum the fp32 partial tiles in a fixed order (deterministic), then the fused epilogue
+// split-K: sum the fp32 partial tiles in a fixed order (deterministic), then the fused epilogue; one quad per thread
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
-  const int chunks_per_row = e.N / 32;
-  const long long total = static_cast<long long>(e.M) * chunks_per_row;
+  pdl_trigger();
+  pdl_wait();
+  const bool geglu = e.epi == DFU_EPI_GEGLU;
+  const int qpr = geglu ? e.N / 8 : e.N / 4;  // quads handled per row
+  const long long total = static_cast<long long>(e.M) * qpr;
+  const size_t plane = static_cast<size_t>(e.M) * e.N;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int m = static_cast<int>(idx / chunks_per_row);
-    const int n = static_cast<int>(idx % chunks_per_row) * 32;
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(s) * e.M + m) * e.N + n);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 t = src[i];
-        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    const int m = static_cast<int>(idx / qpr);
+    const int qi = static_cast<int>(idx % qpr);
+    if (geglu) {
+      const int n_a = (qi >> 2) * 32 + (qi & 3) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+      for (int s = 0; s < splits; ++s) {
+        const float* src = ws + s * plane + static_cast<size_t>(m) * e.N + n_a;
+        const float4 ta = *reinterpret_cast<const float4*>(src);
+        const float4 tg = *reinterpret_cast<const float4*>(src + 16);
+        a.x += ta.x; a.y += ta.y; a.z += ta.z; a.w += ta.w;
+        g.x += tg.x; g.y += tg.y; g.z += tg.z; g.w += tg.w;
       }
+      epi_geglu_quad(e, m, n_a, a, g);
+    } else {
+      const int n = qi * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < splits; ++s) {
+        const float4 t = *reinterpret_cast<const float4*>(ws + s * plane + static_cast<size_t>(m) * e.N + n);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      epi_quad(e, m, n, v);
     }
-    epilogue_chunk32(e, m, n, v);
   }
 }
 
@@ -413,7 +447,7 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
   }
   if (stages > kMaxStages) stages = kMaxStages;
   pl->stages = stages;
-  pl->smem_bytes = stages * stage_bytes + 1024;
+  pl->smem_bytes = stages * stage_bytes + 1024;  // >= kStageBytes: the epilogue staging reuses the ring
   DFU_REQUIRE(pl->smem_bytes <= 226 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
   return DFU_OK;
 }
@@ -531,14 +565,14 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
-  gemm_tc_kernel<<<grid, kGemmThreads, pl.smem_bytes, stream>>>(mA[0], mB[0], mA[1], mB[1], p);
+  DFU_CHECK_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, mA[0], mB[0], mA[1], mB[1], p));
   DFU_CHECK_CUDA(cudaGetLastError());
   if (pl.splits > 1) {
-    const long long total = static_cast<long long>(d->m) * (d->n / 32);
+    const long long total = static_cast<long long>(d->m) * (d->n / 4);
     int blocks = static_cast<int>((total + 255) / 256);
     const int cap = num_sms() > 0 ? num_sms() * 8 : 1184;
     if (blocks > cap) blocks = cap;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, pl.splits, e);
+    DFU_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, p.ws, pl.splits, e));
     DFU_CHECK_CUDA(cudaGetLastError());
   }
   return DFU_OK;

@@ -1,6 +1,7 @@
 // diffute_b200 — host utilities: error text, tensor-map encoding through the driver entry point.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -65,6 +66,15 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     return DFU_ERR_DRIVER;
   }
   return DFU_OK;
+}
+
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFU_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
 }
 
 int num_sms() {

@@ -13,6 +13,8 @@ namespace dfu {
 // ---------------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int B, int dim, int flip_sin_to_cos,
                                       float freq_shift, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim / 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
     const int b = i / half, k = i % half;
@@ -40,6 +42,8 @@ constexpr int kGemvMaxB = 16;
 __global__ void __launch_bounds__(256)
 gemv_kernel(const float* __restrict__ x, int B, int K, int ldx, const float* __restrict__ W,
             const float* __restrict__ bias, int N, int silu_in, int silu_out, float* __restrict__ out, int ldo) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float xs[];  // [B][K] activated input
   for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
     const int b = i / K, k = i % K;
@@ -88,17 +92,22 @@ struct SmallInSrc {
   int nhwc;              // 1: sources are NHWC [B,H,W,c] instead of NCHW
 };
 
+constexpr int kSmallInPix = 16;  // output pixels per CTA
+
 __global__ void __launch_bounds__(256)
-conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const float* __restrict__ w,
+conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const float* __restrict__ wt,
                      const float* __restrict__ bias, int Cout, float pre_scale, float* __restrict__ out) {
-  // block: 64 output pixels (consecutive in a row-major walk) x all Cout; patch staged in smem
-  extern __shared__ float sm[];  // [64][Cin*ksz*ksz]
+  pdl_trigger();
+  pdl_wait();
+  // block: kSmallInPix consecutive output pixels x all Cout; input patches staged in smem; weights are stored
+  // [Cin*k*k][Cout] so that consecutive lanes (consecutive output channels) read consecutive addresses.
+  extern __shared__ float sm[];  // [kSmallInPix][K]
   const int kk = ksz * ksz;
   const int K = Cin * kk;
   const int pad = ksz / 2;
-  const long long pix0 = static_cast<long long>(blockIdx.x) * 64;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * kSmallInPix;
   const long long npix = static_cast<long long>(B) * H * W;
-  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kSmallInPix * K; i += blockDim.x) {
     const int pl = i / K, k = i % K;
     const long long pix = pix0 + pl;
     float v = 0.f;
@@ -120,16 +129,20 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
     sm[i] = v;
   }
   __syncthreads();
-  // thread -> (pixel pl, output channel co) with co fastest for coalesced NHWC stores
-  for (int i = threadIdx.x; i < 64 * Cout; i += blockDim.x) {
-    const int pl = i / Cout, co = i % Cout;
-    const long long pix = pix0 + pl;
-    if (pix >= npix) continue;
-    const float* wr = w + static_cast<size_t>(co) * K;
-    const float* xr = sm + pl * K;
-    float acc = bias ? bias[co] : 0.f;
-    for (int k = 0; k < K; ++k) acc += wr[k] * xr[k];
-    out[pix * Cout + co] = acc;
+  // thread -> output channel co (fastest, coalesced NHWC stores) for a strip of pixels
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc[kSmallInPix];
+    const float b0 = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int j = 0; j < kSmallInPix; ++j) acc[j] = b0;
+    for (int k = 0; k < K; ++k) {
+      const float wv = __ldg(wt + static_cast<size_t>(k) * Cout + co);
+#pragma unroll
+      for (int j = 0; j < kSmallInPix; ++j) acc[j] += wv * sm[j * K + k];
+    }
+#pragma unroll
+    for (int j = 0; j < kSmallInPix; ++j)
+      if (pix0 + j < npix) out[(pix0 + j) * Cout + co] = acc[j];
   }
 }
 
@@ -155,6 +168,8 @@ struct SmallOut {
 };
 
 __global__ void __launch_bounds__(256) conv_small_out_kernel(SmallOut p) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long npix = static_cast<long long>(p.B) * p.H * p.W;
@@ -217,6 +232,8 @@ __global__ void __launch_bounds__(256) conv_small_out_kernel(SmallOut p) {
 __global__ void __launch_bounds__(256)
 axpbypcz_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ n, float a, float b,
                 float c, float* __restrict__ y, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v = a * x[i] + b * e[i];
@@ -231,6 +248,8 @@ __global__ void __launch_bounds__(256)
 sched_step_kernel(const float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ n, float a0,
                   float a1, float p0, float d0, float d1, float sn, int clip, float* __restrict__ y,
                   float* __restrict__ x0_out, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float xv = x[i], mv = m[i];
@@ -247,6 +266,8 @@ sched_step_kernel(const float* __restrict__ x, const float* __restrict__ m, cons
 __global__ void __launch_bounds__(256)
 axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ ca,
                   const float* __restrict__ cb, float* __restrict__ y, long long per_row, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / per_row;
@@ -258,6 +279,8 @@ axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ e, cons
 __global__ void __launch_bounds__(256)
 gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ eps, int B, int Cz, int HW,
                        float scale, float* __restrict__ z) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * Cz * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -281,6 +304,8 @@ gaussian_sample_kernel(const float* __restrict__ moments, const float* __restric
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ s, int rows, int n, int lds, float scale, __half* __restrict__ p16,
                     int ldp, int planes, long long plane_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   if (row >= rows) return;
   __shared__ float red[32];
@@ -314,6 +339,8 @@ softmax_rows_kernel(const float* __restrict__ s, int rows, int n, int lds, float
 // fp16 [planes][rows][cols] -> transposed [planes][cols][rows] (V^T for the VAE attention's P*V GEMM)
 __global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, int ld_in, long long in_plane,
                                      __half* __restrict__ out, long long out_plane) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __half tile[32][33];
   const __half* src = in + blockIdx.z * in_plane;
   __half* dst = out + blockIdx.z * out_plane;
@@ -346,8 +373,7 @@ extern "C" {
 int dfu_timestep_embedding(const float* t, int B, int dim, int flip_sin_to_cos, float freq_shift, float* out,
                            void* stream) {
   DFU_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: B=%d dim=%d", B, dim);
-  timestep_embed_kernel<<<ew_grid2(static_cast<long long>(B) * dim / 2, 128), 128, 0,
-                          static_cast<cudaStream_t>(stream)>>>(t, B, dim, flip_sin_to_cos, freq_shift, out);
+  DFU_CHECK_CUDA(launch_k(timestep_embed_kernel, dim3(ew_grid2(static_cast<long long>(B) * dim / 2, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), t, B, dim, flip_sin_to_cos, freq_shift, out));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -366,8 +392,7 @@ int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float*
   int blocks = (N + 7) / 8;
   const int cap = (num_sms() > 0 ? num_sms() : 148) * 4;
   if (blocks > cap) blocks = cap;
-  gemv_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, B, K, ldx, W, bias, N, silu_in, silu_out,
-                                                                       out, ldo);
+  DFU_CHECK_CUDA(launch_k(gemv_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream), x, B, K, ldx, W, bias, N, silu_in, silu_out, out, ldo));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -383,10 +408,9 @@ int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* 
   s.bstride[0] = bstride0; s.bstride[1] = bstride1; s.bstride[2] = bstride2;
   s.nhwc = nhwc;
   const long long npix = static_cast<long long>(B) * H * W;
-  const int blocks = static_cast<int>((npix + 63) / 64);
-  const size_t smem = 64ull * Cin * ksz * ksz * sizeof(float);
-  conv_small_in_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(s, B, H, W, Cin, ksz, w, bias, Cout,
-                                                                                pre_scale, out);
+  const int blocks = static_cast<int>((npix + kSmallInPix - 1) / kSmallInPix);
+  const size_t smem = static_cast<size_t>(kSmallInPix) * Cin * ksz * ksz * sizeof(float);
+  DFU_CHECK_CUDA(launch_k(conv_small_in_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream), s, B, H, W, Cin, ksz, w, bias, Cout, pre_scale, out));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -405,22 +429,21 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   p.sample = sample; p.prev = prev; p.coef = coef;
   const long long npix = static_cast<long long>(B) * H * W;
   const long long blocks = (npix * 32 + 255) / 256;
-  conv_small_out_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DFU_CHECK_CUDA(launch_k(conv_small_out_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
 
 int dfu_axpbypcz(const float* x, const float* e, const float* n, float a, float b, float c, float* y, int64_t total,
                  void* stream) {
-  axpbypcz_kernel<<<ew_grid2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, e, n, a, b, c, y, total);
+  DFU_CHECK_CUDA(launch_k(axpbypcz_kernel, dim3(ew_grid2(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, e, n, a, b, c, y, total));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
 
 int dfu_scheduler_step(const float* x, const float* m, const float* n, float a0, float a1, float p0, float d0,
                        float d1, float sn, int clip, float* y, float* x0_out, int64_t total, void* stream) {
-  sched_step_kernel<<<ew_grid2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, m, n, a0, a1, p0, d0, d1,
-                                                                                        sn, clip, y, x0_out, total);
+  DFU_CHECK_CUDA(launch_k(sched_step_kernel, dim3(ew_grid2(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, m, n, a0, a1, p0, d0, d1, sn, clip, y, x0_out, total));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -428,25 +451,21 @@ int dfu_scheduler_step(const float* x, const float* m, const float* n, float a0,
 int dfu_axpby_rows(const float* x, const float* e, const float* ca, const float* cb, float* y, int B,
                    int64_t per_row, void* stream) {
   const long long total = static_cast<long long>(B) * per_row;
-  axpby_rows_kernel<<<ew_grid2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, e, ca, cb, y, per_row,
-                                                                                        total);
+  DFU_CHECK_CUDA(launch_k(axpby_rows_kernel, dim3(ew_grid2(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, e, ca, cb, y, per_row, total));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
 
 int dfu_gaussian_sample(const float* moments, const float* eps, int B, int Cz, int HW, float scale, float* z,
                         void* stream) {
-  gaussian_sample_kernel<<<ew_grid2(static_cast<long long>(B) * Cz * HW, 256), 256, 0,
-                           static_cast<cudaStream_t>(stream)>>>(moments, eps, B, Cz, HW, scale, z);
+  DFU_CHECK_CUDA(launch_k(gaussian_sample_kernel, dim3(ew_grid2(static_cast<long long>(B) * Cz * HW, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), moments, eps, B, Cz, HW, scale, z));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
 
 int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void* p16, int ldp, int planes,
                      int64_t plane_stride, void* stream) {
-  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, rows, n, lds, scale,
-                                                                         static_cast<__half*>(p16), ldp, planes,
-                                                                         plane_stride);
+  DFU_CHECK_CUDA(launch_k(softmax_rows_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), s, rows, n, lds, scale, static_cast<__half*>(p16), ldp, planes, plane_stride));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -454,8 +473,7 @@ int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void
 int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int ld_in, int64_t in_plane, void* out,
                       int64_t out_plane, void* stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, planes), block(32, 8);
-  transpose_f16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(in), rows, cols, ld_in, in_plane, static_cast<__half*>(out), out_plane);
+  DFU_CHECK_CUDA(launch_k(transpose_f16_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(in), rows, cols, ld_in, in_plane, static_cast<__half*>(out), out_plane));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -27,6 +27,8 @@ __device__ __forceinline__ float4 gn_load(const GnSrc& s, int b, int pix, int cq
 }
 
 __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [TY][2][C] per-row-of-threads channel sums, reduced in a fixed order (deterministic)
   const int C = s.C0 + s.C1;
   const int cpg = C / groups;
@@ -66,6 +68,8 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
 // per-(sample, group) mean / rstd from the chunk partials, combined in double in a fixed order (deterministic)
 __global__ void gn_finalize_kernel(const float2* __restrict__ partial, int nchunks, int groups, double count, float eps,
                                    float2* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;  // 8 threads per group
   if (g >= groups) return;
@@ -122,6 +126,8 @@ __device__ __forceinline__ void store_split4(__half* dst, long long plane_stride
 }
 
 __global__ void gn_apply_kernel(GnApply a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.s.C0 + a.s.C1;
   const int cpg = C / a.groups;
@@ -171,6 +177,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out16, int planes,
                  long long plane_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -219,6 +227,8 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
 __global__ void __launch_bounds__(256)
 cast_kernel(const float* __restrict__ x, int B, int H, int W, int C, int mode, __half* __restrict__ out, int planes,
             long long plane_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2;
   const long long total = static_cast<long long>(B) * H * W * C4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -293,15 +303,14 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   if (ty > ppc) ty = ppc;
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};
-  gn_stats_kernel<<<grid, block, static_cast<size_t>(ty) * 2 * C * sizeof(float), stream>>>(s, groups, ppc, static_cast<float2*>(workspace));
+  DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), static_cast<size_t>(ty) * 2 * C * sizeof(float), stream, s, groups, ppc, static_cast<float2*>(workspace)));
   DFU_CHECK_CUDA(cudaGetLastError());
   GnApply a;
   a.s = s;
   a.groups = groups;
   a.pix_per_cta = ppc;
   float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
-  gn_finalize_kernel<<<B, 8 * groups, 0, stream>>>(static_cast<const float2*>(workspace), chunks, groups,
-                                                   static_cast<double>(C / groups) * HW, eps, stats);
+  DFU_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(B), dim3(8 * groups), 0, stream, static_cast<const float2*>(workspace), chunks, groups, static_cast<double>(C / groups) * HW, eps, stats));
   DFU_CHECK_CUDA(cudaGetLastError());
   a.stats = stats;
   a.gamma = gamma;
@@ -313,7 +322,7 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   a.plane_stride = plane_stride;
   a.out32 = out32;
   a.raw16 = static_cast<__half*>(raw16);
-  gn_apply_kernel<<<grid, block, 0, stream>>>(a);
+  DFU_CHECK_CUDA(launch_k(gn_apply_kernel, dim3(grid), dim3(block), 0, stream, a));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -323,8 +332,7 @@ int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float*
   DFU_REQUIRE(C % 4 == 0 && C / 4 <= 32 * kLnMaxQuads, "layernorm: C=%d unsupported", C);
   const int warps_per_block = 8;
   const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, warps_per_block * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
-      x, M, C, gamma, beta, eps, static_cast<__half*>(out16), planes, plane_stride);
+  DFU_CHECK_CUDA(launch_k(layernorm_kernel, dim3(blocks), dim3(warps_per_block * 32), 0, static_cast<cudaStream_t>(stream_), x, M, C, gamma, beta, eps, static_cast<__half*>(out16), planes, plane_stride));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -335,8 +343,7 @@ int dfu_cast_f16(const float* x, int B, int H, int W, int C, int mode, void* out
   DFU_REQUIRE(mode >= 0 && mode <= 2, "cast: mode");
   DFU_REQUIRE(!(mode == 2 && ((H | W) & 1)), "cast: space-to-depth needs even H, W");
   const long long total = static_cast<long long>(B) * H * W * (C / 4);
-  cast_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      x, B, H, W, C, mode, static_cast<__half*>(out16), planes, plane_stride);
+  DFU_CHECK_CUDA(launch_k(cast_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream_), x, B, H, W, C, mode, static_cast<__half*>(out16), planes, plane_stride));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -319,10 +319,18 @@ def gemv(x: torch.Tensor, W: torch.Tensor, bias, out: torch.Tensor, silu_in: boo
                              out.data_ptr(), out.stride(0), _stream()), "dfu_gemv")
 
 
-def conv_small_in(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias, out: torch.Tensor, batch: int,
+def pack_small_in_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> fp32 [Cin*k*k, Cout] (transposed so consecutive output channels are contiguous)."""
+    return w.reshape(w.shape[0], -1).t().contiguous()
+
+
+def conv_small_in(srcs: Sequence[torch.Tensor], wt: torch.Tensor, bias, out: torch.Tensor, batch: int,
                   pre_scale: float = 1.0, nhwc: bool = False):
     """srcs: up to 3 fp32 tensors gathered on channels, NCHW [B or 1, c, H, W] (or NHWC [B,H,W,c] with nhwc=True);
-    w [Cout, Cin, k, k]; out NHWC."""
+    wt = pack_small_in_weight(w) [Cin*k*k, Cout]; out NHWC."""
+    cin = sum((s.shape[-1] if nhwc else s.shape[1]) for s in srcs)
+    ksz = 3 if wt.shape[0] == 9 * cin else 1
+    assert wt.shape[0] == cin * ksz * ksz, (wt.shape, cin)
     if nhwc:
         H, W = srcs[0].shape[1:3]
     else:

@@ -171,7 +171,7 @@ class UNet2DConditionModel:
             lin(b + ".ff.net.2")
 
         self.attn_layers = []
-        w["conv_in.w"] = d(sd["conv_in.weight"])
+        w["conv_in.w"] = ops.pack_small_in_weight(d(sd["conv_in.weight"]))
         w["conv_in.b"] = d(sd["conv_in.bias"])
         for n in ("time_embedding.linear_1", "time_embedding.linear_2"):
             w[n + ".w"] = d(sd[n + ".weight"])

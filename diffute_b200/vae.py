@@ -154,6 +154,8 @@ class AutoencoderKL:
             w[a + ".qkv.b"] = torch.cat([d(sd[f"{a}.to_{x}.bias"]) for x in "qkv"], 0)
         w["encoder.conv_out.wp"] = ops.pack_small_out_weight(w["encoder.conv_out.weight"])
         w["decoder.conv_out.wp"] = ops.pack_small_out_weight(w["decoder.conv_out.weight"])
+        for k in ("encoder.conv_in", "post_quant_conv", "decoder.conv_in"):
+            w[k + ".wt"] = ops.pack_small_in_weight(w[k + ".weight"])
         w["quant_conv.w2"] = w["quant_conv.weight"].reshape(w["quant_conv.weight"].shape[0], -1).contiguous()
 
     # ------------------------------------------------------------------------------------------
@@ -238,7 +240,7 @@ class AutoencoderKL:
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         boc = list(cfg["block_out_channels"])
         h = self._fp32([], (B, H, W, boc[0]))
-        ops.conv_small_in([x], w["encoder.conv_in.weight"], w["encoder.conv_in.bias"], h, B)
+        ops.conv_small_in([x], w["encoder.conv_in.wt"], w["encoder.conv_in.bias"], h, B)
         for i, c in enumerate(boc):
             for j in range(cfg["layers_per_block"]):
                 h = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", h, c)
@@ -274,9 +276,9 @@ class AutoencoderKL:
         B, lc, hh, ww = z.shape
         boc = list(cfg["block_out_channels"])[::-1]
         zq = self.arena.get("dec.zq", (B, hh, ww, lc))
-        ops.conv_small_in([z], w["post_quant_conv.weight"], w["post_quant_conv.bias"], zq, B, pre_scale=pre_scale)
+        ops.conv_small_in([z], w["post_quant_conv.wt"], w["post_quant_conv.bias"], zq, B, pre_scale=pre_scale)
         h = self._fp32([], (B, hh, ww, boc[0]))
-        ops.conv_small_in([zq], w["decoder.conv_in.weight"], w["decoder.conv_in.bias"], h, B, nhwc=True)
+        ops.conv_small_in([zq], w["decoder.conv_in.wt"], w["decoder.conv_in.bias"], h, B, nhwc=True)
         h = self._mid("decoder", h)
         for i, c in enumerate(boc):
             for j in range(cfg["layers_per_block"] + 1):

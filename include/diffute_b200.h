@@ -137,7 +137,7 @@ int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float*
 /* Few-input-channel conv (UNet conv_in over the never-materialised cat([latents, mask, masked_latents]) of
  * app.ipynb:811; VAE encoder conv_in; VAE post_quant_conv + decoder conv_in): NCHW fp32 sources -> NHWC fp32.
  * bstrideN: elements between samples of source N (0 broadcasts). nhwc=1: sources are NHWC. pre_scale multiplies
- * the inputs (1/scaling_factor). */
+ * the inputs (1/scaling_factor).  w is TRANSPOSED: [Cin*k*k][Cout] (k = c*k*k + ky*k + kx). */
 int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* src1, int c1, int64_t bstride1,
                       const float* src2, int c2, int64_t bstride2, int nhwc, int B, int H, int W, int ksz,
                       const float* w, const float* bias, int Cout, float pre_scale, float* out, void* stream);

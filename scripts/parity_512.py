@@ -10,7 +10,7 @@ from oracle import DDIMOracle, UNetOracle, VAEOracle, sample_loop
 px = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 modes = sys.argv[3:] or ["mixed", "fp16x2"]
-torch.set_num_threads(os.cpu_count())
+torch.set_num_threads(min(os.cpu_count(), int(os.environ.get('DFU_CPU_THREADS', '32'))))
 usd = synthetic.make_state_dict(arch.unet_param_shapes())
 vsd = synthetic.make_state_dict(arch.vae_param_shapes())
 inp = synthetic.make_inputs(1, px, px)
@@ -20,7 +20,7 @@ t0 = time.time()
 ref = sample_loop(uo, vo, DDIMOracle(), inp["masked_image"], inp["mask"], inp["glyph_embeds"], inp["latents"], steps,
                   posterior_noise=inp["posterior_noise"])
 t_cpu = time.time() - t0
-res = {"px": px, "steps": steps, "cpu_oracle_seconds": t_cpu, "cpu_cores": os.cpu_count(), "modes": {}}
+res = {"px": px, "steps": steps, "cpu_oracle_seconds": t_cpu, "cpu_threads": torch.get_num_threads(), "modes": {}}
 for m in modes:
     up, vp = {"mixed": ("fp16", "fp16x2"), "fp16x2": ("fp16x2", "fp16x2"), "fp16": ("fp16", "fp16")}[m]
     pipe = DiffUTEPipeline.from_synthetic(up, vp, state_dicts=(usd, vsd))

@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+    # the CPU oracle regresses badly when torch grabs all 128 hardware threads of the GPU box's host
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 32)))
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     config.addinivalue_line("markers", "slow: long CPU test")
 

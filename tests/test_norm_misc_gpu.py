@@ -107,14 +107,14 @@ def test_conv_small_in_out(ops):
     w = _rand((320, 9, 3, 3), 15, 81 ** -0.5)
     bias = _rand((320,), 16)
     out = torch.zeros((B, H, W, 320), device="cuda")
-    ops.conv_small_in([lat, mask, ml], w, bias, out, B)
+    ops.conv_small_in([lat, mask, ml], ops.pack_small_in_weight(w), bias, out, B)
     x = torch.cat([lat, mask.expand(B, -1, -1, -1), ml], 1)
     ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
     assert _rel(out, ref) < 1e-5
     # 1x1 with pre-scale (post_quant_conv on latents / scaling_factor)
     w1 = _rand((4, 4, 1, 1), 17)
     o1 = torch.zeros((B, H, W, 4), device="cuda")
-    ops.conv_small_in([lat], w1, None, o1, B, pre_scale=1 / 0.18215)
+    ops.conv_small_in([lat], ops.pack_small_in_weight(w1), None, o1, B, pre_scale=1 / 0.18215)
     ref = F.conv2d(lat.double() / 0.18215, w1.double()).permute(0, 2, 3, 1)
     assert _rel(o1, ref) < 1e-5
     # few-output conv with fused scheduler step and trailing 1x1

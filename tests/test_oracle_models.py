@@ -14,7 +14,6 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracl
 
 @pytest.fixture(scope="module")
 def models():
-    torch.set_num_threads(os.cpu_count())
     u, v = UNetOracle(), VAEOracle()
     u.load_state_dict(synthetic.make_state_dict(arch.unet_param_shapes()))
     v.load_state_dict(synthetic.make_state_dict(arch.vae_param_shapes()))
