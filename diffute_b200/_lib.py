@@ -38,6 +38,7 @@ class Gemm(C.Structure):
         ("out_f16", C.c_void_p), ("ldh", C.c_int32), ("out_planes", C.c_int32), ("out_plane_stride", C.c_int64),
         ("block_n", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("tile_counters", C.c_void_p), ("tile_counters_len", C.c_int32),
     ]
 
 

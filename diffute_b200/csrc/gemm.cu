@@ -53,6 +53,7 @@ struct GemmKernelParams {
   uint32_t b_tx_bytes;
   uint32_t tmem_cols;
   float* ws;
+  int* counters;  // per-output-tile arrival counters for split-K (zero before and after every launch)
   EpiParams e;
 };
 
@@ -130,6 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ int split_flag;
 
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -302,9 +304,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
           if (vr) {
             if (p.splits > 1)
-              *reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mr) * p.e.N + n + cq * 4) = v;
+              __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mr) * p.e.N + n + cq * 4), v);
             else
               epi_quad(p.e, mr, n + cq * 4, v);
+          }
+        }
+      }
+    }
+    if (p.splits > 1) {
+      // Split-K without a second launch: every slice parks its fp32 partial tile in the (L2-resident) workspace and
+      // bumps the tile's arrival counter; the LAST slice to arrive sums all partials in slice order (deterministic
+      // whatever the arrival order) and runs the fused epilogue.  The counter is left at zero for the next launch.
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {  // first epilogue thread
+        __threadfence();
+        const int tile_id = tm * p.tiles_n + tn;
+        const int prev = atomicAdd(p.counters + tile_id, 1);
+        const int last = (prev == p.splits - 1) ? 1 : 0;
+        if (last) p.counters[tile_id] = 0;
+        __threadfence();
+        split_flag = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (split_flag) {
+        const size_t plane = static_cast<size_t>(p.e.M) * p.e.N;
+        for (int c = 0; c < p.block_n; c += 32) {
+          const int n = n_tile0 + c;
+          if (p.e.epi == DFU_EPI_GEGLU) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int row = it * 8 + (lane >> 2), cq = lane & 3;
+              const int mr = __shfl_sync(0xffffffffu, m, row);
+              const int vr = __shfl_sync(0xffffffffu, vmask, row);
+              if (vr) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+                const float* src = p.ws + static_cast<size_t>(mr) * p.e.N + n + cq * 4;
+                for (int sidx = 0; sidx < p.splits; ++sidx) {
+                  const float4 ta = __ldcg(reinterpret_cast<const float4*>(src + sidx * plane));
+                  const float4 tg = __ldcg(reinterpret_cast<const float4*>(src + sidx * plane + 16));
+                  a.x += ta.x; a.y += ta.y; a.z += ta.z; a.w += ta.w;
+                  g.x += tg.x; g.y += tg.y; g.z += tg.z; g.w += tg.w;
+                }
+                epi_geglu_quad(p.e, mr, n + cq * 4, a, g);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3), cq = lane & 7;
+              const int mr = __shfl_sync(0xffffffffu, m, row);
+              const int vr = __shfl_sync(0xffffffffu, vmask, row);
+              if (vr) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* src = p.ws + static_cast<size_t>(mr) * p.e.N + n + cq * 4;
+                for (int sidx = 0; sidx < p.splits; ++sidx) {
+                  const float4 t = __ldcg(reinterpret_cast<const float4*>(src + sidx * plane));
+                  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                }
+                epi_quad(p.e, mr, n + cq * 4, v);
+              }
+            }
           }
         }
       }
@@ -316,41 +376,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
-  }
-}
-
-// split-K: sum the fp32 partial tiles in a fixed order (deterministic), then the fused epilogue; one quad per thread
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
-  pdl_trigger();
-  pdl_wait();
-  const bool geglu = e.epi == DFU_EPI_GEGLU;
-  const int qpr = geglu ? e.N / 8 : e.N / 4;  // quads handled per row
-  const long long total = static_cast<long long>(e.M) * qpr;
-  const size_t plane = static_cast<size_t>(e.M) * e.N;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int m = static_cast<int>(idx / qpr);
-    const int qi = static_cast<int>(idx % qpr);
-    if (geglu) {
-      const int n_a = (qi >> 2) * 32 + (qi & 3) * 4;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-      for (int s = 0; s < splits; ++s) {
-        const float* src = ws + s * plane + static_cast<size_t>(m) * e.N + n_a;
-        const float4 ta = *reinterpret_cast<const float4*>(src);
-        const float4 tg = *reinterpret_cast<const float4*>(src + 16);
-        a.x += ta.x; a.y += ta.y; a.z += ta.z; a.w += ta.w;
-        g.x += tg.x; g.y += tg.y; g.z += tg.z; g.w += tg.w;
-      }
-      epi_geglu_quad(e, m, n_a, a, g);
-    } else {
-      const int n = qi * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < splits; ++s) {
-        const float4 t = *reinterpret_cast<const float4*>(ws + s * plane + static_cast<size_t>(m) * e.N + n);
-        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-      }
-      epi_quad(e, m, n, v);
-    }
   }
 }
 
@@ -488,6 +513,10 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
       set_error("gemm: split-K needs %zu workspace bytes, got %zu", pl.ws_bytes, d->workspace_bytes);
       return DFU_ERR_WORKSPACE;
     }
+    if (!d->tile_counters || d->tile_counters_len < pl.tiles_m * pl.tiles_n) {
+      set_error("gemm: split-K needs %d zeroed tile counters, got %d", pl.tiles_m * pl.tiles_n, d->tile_counters_len);
+      return DFU_ERR_WORKSPACE;
+    }
   }
   DFU_REQUIRE(d->epi >= 0 && d->epi <= 2, "gemm: bad epi");
   if (d->epi == DFU_EPI_F32) DFU_REQUIRE(d->out_f32 && d->ldo % 4 == 0, "gemm: out_f32/ldo");
@@ -541,6 +570,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   while (cols < static_cast<uint32_t>(pl.block_n)) cols <<= 1;
   p.tmem_cols = cols;
   p.ws = static_cast<float*>(d->workspace);
+  p.counters = d->tile_counters;
   EpiParams& e = p.e;
   e.M = d->m;
   e.N = d->n;
@@ -567,14 +597,6 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
   DFU_CHECK_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, mA[0], mB[0], mA[1], mB[1], p));
   DFU_CHECK_CUDA(cudaGetLastError());
-  if (pl.splits > 1) {
-    const long long total = static_cast<long long>(d->m) * (d->n / 4);
-    int blocks = static_cast<int>((total + 255) / 256);
-    const int cap = num_sms() > 0 ? num_sms() * 8 : 1184;
-    if (blocks > cap) blocks = cap;
-    DFU_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, p.ws, pl.splits, e));
-    DFU_CHECK_CUDA(cudaGetLastError());
-  }
   return DFU_OK;
 }
 

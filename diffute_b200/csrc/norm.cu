@@ -99,7 +99,10 @@ struct GnApply {
   GnSrc s;
   int groups;
   int pix_per_cta;
-  const float2* stats;    // [B][groups] (mean, rstd)
+  const float2* stats;    // [B][groups] (mean, rstd) from gn_finalize_kernel, or null:
+  const float2* partial;  // ... then every CTA combines the `nchunks` chunk partials itself (few chunks: cheaper
+  int nchunks;            //     than a third launch)
+  double count;
   const float* gamma;
   const float* beta;
   float eps;
@@ -133,10 +136,35 @@ __global__ void gn_apply_kernel(GnApply a) {
   const int cpg = C / a.groups;
   const int b = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (tid < a.groups) {
-    const float2 t = a.stats[b * a.groups + tid];
-    s_mean[tid] = t.x;
-    s_rstd[tid] = t.y;
+  if (a.stats) {
+    if (tid < a.groups) {
+      const float2 t = a.stats[b * a.groups + tid];
+      s_mean[tid] = t.x;
+      s_rstd[tid] = t.y;
+    }
+  } else {
+    // same arithmetic and order as gn_finalize_kernel: 8 threads per group, fixed-order double accumulation
+    const int g = tid >> 3, sub = tid & 7;
+    if (g < a.groups) {
+      double sum = 0.0, sq = 0.0;
+      for (int k = sub; k < a.nchunks; k += 8) {
+        const float2 t = a.partial[(static_cast<size_t>(b) * a.nchunks + k) * a.groups + g];
+        sum += t.x;
+        sq += t.y;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if (sub == 0) {
+        const double mean = sum / a.count;
+        double var = sq / a.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + a.eps));
+      }
+    }
   }
   __syncthreads();
   const int c = threadIdx.x * 4;
@@ -309,10 +337,16 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   a.s = s;
   a.groups = groups;
   a.pix_per_cta = ppc;
-  float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
-  DFU_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(B), dim3(8 * groups), 0, stream, static_cast<const float2*>(workspace), chunks, groups, static_cast<double>(C / groups) * HW, eps, stats));
-  DFU_CHECK_CUDA(cudaGetLastError());
-  a.stats = stats;
+  a.partial = static_cast<const float2*>(workspace);
+  a.nchunks = chunks;
+  a.count = static_cast<double>(C / groups) * HW;
+  a.stats = nullptr;
+  const bool inline_finalize = chunks <= 64 && static_cast<int>(block.x * block.y) >= 8 * groups;
+  if (!inline_finalize) {
+    float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
+    DFU_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(B), dim3(8 * groups), 0, stream, static_cast<const float2*>(workspace), chunks, groups, a.count, eps, stats));
+    a.stats = stats;
+  }
   a.gamma = gamma;
   a.beta = beta;
   a.eps = eps;

@@ -131,6 +131,8 @@ class Workspace:
         self.device = device
         self.generation = 0  # bumped on every reallocation: captured CUDA graphs holding the old address are stale
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+        # split-K arrival counters: zeroed once here; every launch leaves them zero again
+        self.counters = torch.zeros(16384, dtype=torch.int32, device=device)
 
     def ensure(self, nbytes: int):
         if self.buf.numel() < nbytes:
@@ -196,8 +198,10 @@ def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
         buf = ws.ensure(need)
         d.workspace = buf.data_ptr()
         d.workspace_bytes = buf.numel()
+        d.tile_counters = ws.counters.data_ptr()
+        d.tile_counters_len = ws.counters.numel()
     k = sum(d.g[i].ntaps * d.g[i].k_per_tap for i in range(d.ngroups))
-    with _Prof("gemm_conv" if d.conv else "gemm_linear", 2 if need else 1, 2.0 * d.m * d.n * k):
+    with _Prof("gemm_conv" if d.conv else "gemm_linear", 1, 2.0 * d.m * d.n * k):
         check(L.dfu_gemm(C.byref(d), _stream()), "dfu_gemm")
 
 
@@ -343,7 +347,7 @@ def conv_small_in(srcs: Sequence[torch.Tensor], wt: torch.Tensor, bias, out: tor
         else:
             a += [None, 0, 0]
     with _Prof('conv_small_in', 1):
-        check(lib().dfu_conv_small_in(*a, int(nhwc), batch, H, W, w.shape[-1], w.data_ptr(), _ptr(bias), w.shape[0],
+        check(lib().dfu_conv_small_in(*a, int(nhwc), batch, H, W, ksz, wt.data_ptr(), _ptr(bias), wt.shape[1],
                                       pre_scale, out.data_ptr(), _stream()), "dfu_conv_small_in")
 
 

@@ -99,6 +99,8 @@ typedef struct DfuGemm {
   int32_t stages;
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
   size_t workspace_bytes;
+  int32_t* tile_counters;  /* split-K arrival counters, one per output tile: ZERO on entry, left zero on exit */
+  int32_t tile_counters_len;
 } DfuGemm;
 
 int dfu_gemm(const DfuGemm* desc, void* stream);
