@@ -38,7 +38,6 @@ class Gemm(C.Structure):
         ("out_f16", C.c_void_p), ("ldh", C.c_int32), ("out_planes", C.c_int32), ("out_plane_stride", C.c_int64),
         ("block_n", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-        ("tile_counters", C.c_void_p), ("tile_counters_len", C.c_int32),
     ]
 
 
@@ -62,6 +61,8 @@ def lib() -> C.CDLL:
     L.dfu_num_sms.restype = C.c_int
     L.dfu_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
     L.dfu_gemm.restype = C.c_int
+    L.dfu_gemm_plan.argtypes = [C.POINTER(Gemm), C.POINTER(C.c_int32)]
+    L.dfu_gemm_plan.restype = C.c_int
     L.dfu_gemm_workspace.argtypes = [C.POINTER(Gemm)]
     L.dfu_gemm_workspace.restype = C.c_size_t
     _declare_rest(L)

@@ -44,19 +44,27 @@ __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   pdl_trigger();
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2];
-  __shared__ __align__(8) uint64_t s_full, s_free, p_full, o_full, o_free;
-  __shared__ uint32_t tmem_base_smem;
-
-  uint8_t* smem =
-      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // No static shared memory: the dynamic window then starts 1024-byte aligned at the CTA's base, and the FP16 mode
+  // needs 7 x 16 KiB + 128 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int planes = p.planes;
-  // layout: Q[planes] | K[2][planes] | V[2][planes] | P[planes][2 tiles]
+  // layout: Q[planes] | K[2][planes] | V[2][planes] | P[planes][2 tiles] | barriers
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + planes * kTile;
   uint8_t* sV = sK + 2 * planes * kTile;
   uint8_t* sP = sV + 2 * planes * kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * planes * kTile);
+  uint64_t& q_full = bars[0];
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t& s_full = bars[9];
+  uint64_t& s_free = bars[10];
+  uint64_t& p_full = bars[11];
+  uint64_t& o_full = bars[12];
+  uint64_t& o_free = bars[13];
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -224,21 +232,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint8_t* tile_lo = sP + (2 + (c >> 1)) * kTile + prow;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {  // 16-byte units of 8 probabilities
-          __align__(16) __half h[8];
-          __align__(16) __half lo[8];
+          float pv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int col = c * 32 + u * 8 + i;
-            float pv = fast_exp2(__uint_as_float(raw[u * 8 + i]) * c2 - mc);
-            pv = (col < kv_valid) ? pv : 0.f;
-            rowsum += pv;
-            h[i] = __float2half_rn(pv);
-            lo[i] = __float2half_rn(pv - __half2float(h[i]));
+            const float e = fast_exp2(__uint_as_float(raw[u * 8 + i]) * c2 - mc);
+            pv[i] = (col < kv_valid) ? e : 0.f;
+            rowsum += pv[i];
           }
+          __align__(16) __half2 h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
           const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u);
           const uint32_t off = (unit ^ sw) << 4;
           *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
-          if (planes == 2) *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+          if (planes == 2) {
+            __align__(16) __half2 lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 hf = __half22float2(h[i]);
+              lo[i] = __floats2half2_rn(pv[2 * i] - hf.x, pv[2 * i + 1] - hf.y);
+            }
+            *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+          }
         }
       }
       tc_fence_before();
@@ -256,16 +272,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        __align__(16) __half h[8];
-        __align__(16) __half lo[8];
+        __align__(16) __half2 h[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float v = acc[u * 8 + i] * inv;
-          h[i] = __float2half_rn(v);
-          lo[i] = __float2half_rn(v - __half2float(h[i]));
-        }
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(acc[u * 8 + 2 * i] * inv, acc[u * 8 + 2 * i + 1] * inv);
         *reinterpret_cast<uint4*>(dst + u * 8) = *reinterpret_cast<const uint4*>(h);
-        if (planes == 2) *reinterpret_cast<uint4*>(dst + p.out_plane_stride + u * 8) = *reinterpret_cast<const uint4*>(lo);
+        if (planes == 2) {
+          __align__(16) __half2 lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 hf = __half22float2(h[i]);
+            lo[i] = __floats2half2_rn(acc[u * 8 + 2 * i] * inv - hf.x, acc[u * 8 + 2 * i + 1] * inv - hf.y);
+          }
+          *reinterpret_cast<uint4*>(dst + p.out_plane_stride + u * 8) = *reinterpret_cast<const uint4*>(lo);
+        }
       }
     }
   }
@@ -311,7 +330,7 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   p.out = static_cast<__half*>(out);
   p.ldo = ldo;
   p.out_plane_stride = out_plane_stride;
-  const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 1024;
+  const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 128;
   static bool attr = false;
   if (!attr) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

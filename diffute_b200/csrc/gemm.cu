@@ -53,7 +53,6 @@ struct GemmKernelParams {
   uint32_t b_tx_bytes;
   uint32_t tmem_cols;
   float* ws;
-  int* counters;  // per-output-tile arrival counters for split-K (zero before and after every launch)
   EpiParams e;
 };
 
@@ -131,7 +130,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ int split_flag;
 
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -311,64 +309,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
-    if (p.splits > 1) {
-      // Split-K without a second launch: every slice parks its fp32 partial tile in the (L2-resident) workspace and
-      // bumps the tile's arrival counter; the LAST slice to arrive sums all partials in slice order (deterministic
-      // whatever the arrival order) and runs the fused epilogue.  The counter is left at zero for the next launch.
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {  // first epilogue thread
-        __threadfence();
-        const int tile_id = tm * p.tiles_n + tn;
-        const int prev = atomicAdd(p.counters + tile_id, 1);
-        const int last = (prev == p.splits - 1) ? 1 : 0;
-        if (last) p.counters[tile_id] = 0;
-        __threadfence();
-        split_flag = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (split_flag) {
-        const size_t plane = static_cast<size_t>(p.e.M) * p.e.N;
-        for (int c = 0; c < p.block_n; c += 32) {
-          const int n = n_tile0 + c;
-          if (p.e.epi == DFU_EPI_GEGLU) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int row = it * 8 + (lane >> 2), cq = lane & 3;
-              const int mr = __shfl_sync(0xffffffffu, m, row);
-              const int vr = __shfl_sync(0xffffffffu, vmask, row);
-              if (vr) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-                const float* src = p.ws + static_cast<size_t>(mr) * p.e.N + n + cq * 4;
-                for (int sidx = 0; sidx < p.splits; ++sidx) {
-                  const float4 ta = __ldcg(reinterpret_cast<const float4*>(src + sidx * plane));
-                  const float4 tg = __ldcg(reinterpret_cast<const float4*>(src + sidx * plane + 16));
-                  a.x += ta.x; a.y += ta.y; a.z += ta.z; a.w += ta.w;
-                  g.x += tg.x; g.y += tg.y; g.z += tg.z; g.w += tg.w;
-                }
-                epi_geglu_quad(p.e, mr, n + cq * 4, a, g);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + (lane >> 3), cq = lane & 7;
-              const int mr = __shfl_sync(0xffffffffu, m, row);
-              const int vr = __shfl_sync(0xffffffffu, vmask, row);
-              if (vr) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float* src = p.ws + static_cast<size_t>(mr) * p.e.N + n + cq * 4;
-                for (int sidx = 0; sidx < p.splits; ++sidx) {
-                  const float4 t = __ldcg(reinterpret_cast<const float4*>(src + sidx * plane));
-                  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                }
-                epi_quad(p.e, mr, n + cq * 4, v);
-              }
-            }
-          }
-        }
-      }
-    }
   }
 
   tc_fence_before();
@@ -376,6 +316,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// split-K second stage: every thread owns one output quad, sums the `splits` fp32 partials in slice order
+// (deterministic), four independent 16-byte loads in flight at a time, then runs the fused epilogue.
+__device__ __forceinline__ float4 sum_partials(const float* __restrict__ src, size_t plane, int splits) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + (s + 0) * plane));
+    const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + (s + 1) * plane));
+    const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + (s + 2) * plane));
+    const float4 t3 = __ldcg(reinterpret_cast<const float4*>(src + (s + 3) * plane));
+    v.x = (((v.x + t0.x) + t1.x) + t2.x) + t3.x;
+    v.y = (((v.y + t0.y) + t1.y) + t2.y) + t3.y;
+    v.z = (((v.z + t0.z) + t1.z) + t2.z) + t3.z;
+    v.w = (((v.w + t0.w) + t1.w) + t2.w) + t3.w;
+  }
+  for (; s < splits; ++s) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + s * plane));
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
+  pdl_trigger();
+  pdl_wait();
+  const bool geglu = e.epi == DFU_EPI_GEGLU;
+  const int qpr = geglu ? e.N / 8 : e.N / 4;  // quads handled per row
+  const long long total = static_cast<long long>(e.M) * qpr;
+  const size_t plane = static_cast<size_t>(e.M) * e.N;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / qpr);
+    const int qi = static_cast<int>(idx % qpr);
+    if (geglu) {
+      const int n_a = (qi >> 2) * 32 + (qi & 3) * 4;
+      const float* src = ws + static_cast<size_t>(m) * e.N + n_a;
+      epi_geglu_quad(e, m, n_a, sum_partials(src, plane, splits), sum_partials(src + 16, plane, splits));
+    } else {
+      const int n = qi * 4;
+      epi_quad(e, m, n, sum_partials(ws + static_cast<size_t>(m) * e.N + n, plane, splits));
+    }
   }
 }
 
@@ -431,37 +415,47 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
   }
   const int sms = num_sms() > 0 ? num_sms() : 148;
   int bn_ = d->block_n;
-  if (bn_ <= 0) {
+  int splits = d->splits;
+  if (bn_ <= 0 || splits <= 0) {
+    // Cost model (SM cycles).  Per K=16 step a 128 x bn tile costs max(tensor, smem): the tensor pipe needs bn/2
+    // cycles, the SS-mode operand fetch (4 KiB of A + 32*bn bytes of B at 128 B/clk) 32 + bn/4 — so tiles narrower
+    // than 128 columns are operand-bandwidth bound and parallelism is bought with split-K instead.  CTAs beyond one
+    // per SM serialise on the tensor pipe; a split adds a partial-tile round trip through L2 and a second launch.
     const int cands[] = {256, 160, 128, 96, 64, 32};
-    bn_ = 0;
-    // widest tile that still leaves enough CTAs; otherwise the widest that divides n
-    for (int c : cands)
-      if (d->n % c == 0 && pl->tiles_m * (d->n / c) >= sms - 28) {
-        bn_ = c;
-        break;
-      }
-    if (!bn_)
-      for (int c : cands)
-        if (d->n % c == 0 && c <= 160) {
-          bn_ = c;
-          break;
+    const int scand[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+    double best = 1e30;
+    int best_bn = 0, best_s = 1;
+    for (int c : cands) {
+      if (d->n % c != 0) continue;
+      if (d->block_n > 0 && c != d->block_n) continue;
+      const int tiles = pl->tiles_m * (d->n / c);
+      const double per_k16 = (c / 2.0 > 32.0 + c / 4.0) ? c / 2.0 : 32.0 + c / 4.0;
+      for (int sp : scand) {
+        if (d->splits > 0 && sp != d->splits) continue;
+        if (sp > 1 && total_kb / sp < 2) continue;
+        const int ctas = tiles * sp;
+        const int kb = (total_kb + sp - 1) / sp;
+        const double cta = 2500.0 + kb * 4.0 * per_k16 + (c / 32) * 450.0;  // prologue/fill + main loop + epilogue
+        const double rounds = static_cast<double>((ctas + sms - 1) / sms);
+        double t = rounds * cta;
+        if (sp > 1) {
+          const double bytes = 2.0 * sp * static_cast<double>(d->m) * d->n * 4.0;  // partials written and re-read
+          t += 4000.0 + bytes / 1500.0;                                             // launch + ~3 TB/s of L2
         }
-    if (!bn_) bn_ = 32;
+        if (t < best) {
+          best = t;
+          best_bn = c;
+          best_s = sp;
+        }
+      }
+    }
+    DFU_REQUIRE(best_bn > 0, "gemm: no tiling for n=%d (block_n=%d splits=%d)", d->n, d->block_n, d->splits);
+    bn_ = best_bn;
+    splits = best_s;
   }
   DFU_REQUIRE(bn_ % 32 == 0 && bn_ <= 256 && d->n % bn_ == 0, "gemm: bad block_n=%d for n=%d", bn_, d->n);
   pl->block_n = bn_;
   pl->tiles_n = d->n / bn_;
-  int splits = d->splits;
-  if (splits <= 0) {
-    const int tiles = pl->tiles_m * pl->tiles_n;
-    splits = 1;
-    if (tiles < sms * 3 / 4) {
-      splits = (sms + tiles - 1) / tiles;
-      const int max_by_k = total_kb / 4 > 0 ? total_kb / 4 : 1;
-      if (splits > max_by_k) splits = max_by_k;
-      if (splits > 32) splits = 32;
-    }
-  }
   DFU_REQUIRE(splits >= 1 && splits <= total_kb, "gemm: bad splits=%d (k-blocks %d)", splits, total_kb);
   pl->splits = splits;
   pl->ws_bytes = splits > 1 ? static_cast<size_t>(splits) * d->m * d->n * sizeof(float) : 0;
@@ -511,10 +505,6 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   if (pl.splits > 1) {
     if (!d->workspace || d->workspace_bytes < pl.ws_bytes) {
       set_error("gemm: split-K needs %zu workspace bytes, got %zu", pl.ws_bytes, d->workspace_bytes);
-      return DFU_ERR_WORKSPACE;
-    }
-    if (!d->tile_counters || d->tile_counters_len < pl.tiles_m * pl.tiles_n) {
-      set_error("gemm: split-K needs %d zeroed tile counters, got %d", pl.tiles_m * pl.tiles_n, d->tile_counters_len);
       return DFU_ERR_WORKSPACE;
     }
   }
@@ -570,7 +560,6 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   while (cols < static_cast<uint32_t>(pl.block_n)) cols <<= 1;
   p.tmem_cols = cols;
   p.ws = static_cast<float*>(d->workspace);
-  p.counters = d->tile_counters;
   EpiParams& e = p.e;
   e.M = d->m;
   e.N = d->n;
@@ -597,6 +586,13 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
   DFU_CHECK_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, mA[0], mB[0], mA[1], mB[1], p));
   DFU_CHECK_CUDA(cudaGetLastError());
+  if (pl.splits > 1) {
+    const long long total = static_cast<long long>(d->m) * (d->n / (d->epi == DFU_EPI_GEGLU ? 8 : 4));
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    DFU_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p.ws, pl.splits, e));
+  }
   return DFU_OK;
 }
 
@@ -609,6 +605,15 @@ int dfu_gemm(const DfuGemm* desc, void* stream) {
     return DFU_ERR_INVALID;
   }
   return dfu::run_gemm(desc, static_cast<cudaStream_t>(stream));
+}
+int dfu_gemm_plan(const DfuGemm* desc, int32_t* out) {
+  dfu::Plan pl;
+  if (!desc || !out) return DFU_ERR_INVALID;
+  int rc = dfu::plan_gemm(desc, &pl);
+  if (rc) return rc;
+  out[0] = pl.block_n; out[1] = pl.splits; out[2] = pl.stages; out[3] = pl.tiles_m; out[4] = pl.tiles_n;
+  out[5] = pl.total_kb;
+  return DFU_OK;
 }
 size_t dfu_gemm_workspace(const DfuGemm* desc) {
   dfu::Plan pl;

@@ -13,6 +13,8 @@ namespace dfu {
 // GroupNorm statistics: per (sample, pixel-chunk, group) partial sum / sum of squares
 //   grid (chunks, B), block (C/4, TY).  Thread (tx, ty) owns channel quad tx for pixels ty, ty+TY, ...
 // =============================================================================================
+constexpr int kGnPixPerThread = 4;
+
 struct GnSrc {
   const float* src0;
   const float* src1;  // optional second tensor of a channel concat ([h, skip] in the up blocks)
@@ -37,12 +39,19 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
   const int p1 = min(p0 + pix_per_cta, s.HW);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   float sx[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const float4 v = gn_load(s, b, p, threadIdx.x);
-    sx[0] += v.x; sq[0] += v.x * v.x;
-    sx[1] += v.y; sq[1] += v.y * v.y;
-    sx[2] += v.z; sq[2] += v.z * v.z;
-    sx[3] += v.w; sq[3] += v.w * v.w;
+  // <= kGnPixPerThread pixels per thread, all loads issued before the first use (memory-level parallelism)
+  float4 v[kGnPixPerThread];
+#pragma unroll
+  for (int j = 0; j < kGnPixPerThread; ++j) {
+    const int p = p0 + threadIdx.y + j * blockDim.y;
+    v[j] = (p < p1) ? gn_load(s, b, p, threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < kGnPixPerThread; ++j) {
+    sx[0] += v[j].x; sq[0] += v[j].x * v[j].x;
+    sx[1] += v[j].y; sq[1] += v[j].y * v[j].y;
+    sx[2] += v[j].z; sq[2] += v[j].z * v[j].z;
+    sx[3] += v[j].w; sq[3] += v[j].w * v[j].w;
   }
   const int c = threadIdx.x * 4;
   float* mine = sm + static_cast<size_t>(threadIdx.y) * 2 * C;
@@ -179,8 +188,17 @@ __global__ void gn_apply_kernel(GnApply a) {
   }
   const int p0 = blockIdx.x * a.pix_per_cta;
   const int p1 = min(p0 + a.pix_per_cta, a.s.HW);
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const float4 v = gn_load(a.s, b, p, threadIdx.x);
+  float4 vin[kGnPixPerThread];
+#pragma unroll
+  for (int j = 0; j < kGnPixPerThread; ++j) {
+    const int p = p0 + threadIdx.y + j * blockDim.y;
+    vin[j] = (p < p1) ? gn_load(a.s, b, p, threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < kGnPixPerThread; ++j) {
+    const int p = p0 + threadIdx.y + j * blockDim.y;
+    if (p >= p1) break;
+    const float4 v = vin[j];
     float4 y;
     y.x = (v.x - mu[0]) * rs[0] * ga[0] + be[0];
     y.y = (v.y - mu[1]) * rs[1] * ga[1] + be[1];
@@ -300,12 +318,23 @@ static int ew_grid(long long total, int threads) {
 
 using namespace dfu;
 
+// block (C/4, ty), ty rows of threads each walking kGnPixPerThread pixels -> ppc pixels per CTA
+static void gn_geometry(int HW, int C, int* ty, int* ppc, int* chunks) {
+  const int C4 = C / 4;
+  int t = 512 / C4;
+  if (t < 1) t = 1;
+  if (t > 16) t = 16;
+  if (t > HW) t = HW;
+  *ty = t;
+  *ppc = t * kGnPixPerThread;
+  *chunks = (HW + *ppc - 1) / *ppc;
+}
+
 extern "C" {
 
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups) {
-  (void)C;
-  const int ppc = HW >= 65536 ? 256 : (HW >= 4096 ? 64 : (HW >= 1024 ? 32 : 16));
-  const int chunks = (HW + ppc - 1) / ppc;
+  int ty, ppc, chunks;
+  gn_geometry(HW, C, &ty, &ppc, &chunks);
   return static_cast<size_t>(B) * (chunks + 1) * groups * sizeof(float2);
 }
 
@@ -323,12 +352,9 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
     set_error("groupnorm: workspace %zu < %zu", workspace_bytes, need);
     return DFU_ERR_WORKSPACE;
   }
-  const int ppc = HW >= 65536 ? 256 : (HW >= 4096 ? 64 : (HW >= 1024 ? 32 : 16));
-  const int chunks = (HW + ppc - 1) / ppc;
+  int ty, ppc, chunks;
+  gn_geometry(HW, C, &ty, &ppc, &chunks);
   const int C4 = C / 4;
-  int ty = 512 / C4;
-  if (ty < 1) ty = 1;
-  if (ty > ppc) ty = ppc;
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};
   DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), static_cast<size_t>(ty) * 2 * C * sizeof(float), stream, s, groups, ppc, static_cast<float2*>(workspace)));
@@ -341,7 +367,7 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   a.nchunks = chunks;
   a.count = static_cast<double>(C / groups) * HW;
   a.stats = nullptr;
-  const bool inline_finalize = chunks <= 64 && static_cast<int>(block.x * block.y) >= 8 * groups;
+  const bool inline_finalize = chunks <= 256 && static_cast<int>(block.x * block.y) >= 8 * groups;
   if (!inline_finalize) {
     float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
     DFU_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(B), dim3(8 * groups), 0, stream, static_cast<const float2*>(workspace), chunks, groups, a.count, eps, stats));

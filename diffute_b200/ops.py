@@ -6,6 +6,8 @@ libdiffute_b200.so and raises DfuError on failure; nothing falls back to torch a
 from __future__ import annotations
 
 import ctypes as C
+import json
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -131,8 +133,6 @@ class Workspace:
         self.device = device
         self.generation = 0  # bumped on every reallocation: captured CUDA graphs holding the old address are stale
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
-        # split-K arrival counters: zeroed once here; every launch leaves them zero again
-        self.counters = torch.zeros(16384, dtype=torch.int32, device=device)
 
     def ensure(self, nbytes: int):
         if self.buf.numel() < nbytes:
@@ -190,18 +190,42 @@ def image_operand(op, a16: torch.Tensor, w16: torch.Tensor, planes: int, taps, i
     _fill_taps(op, taps)
 
 
+# ---------------------------------------------------------------------------------------------
+# per-shape tiling table (measured on B200 by scripts/tune_gemm.py; the C cost model is the fallback)
+# ---------------------------------------------------------------------------------------------
+TUNE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning_b200.json")
+TUNE_TABLE = {}
+TUNER = None  # set to a callable (d, ws, key) -> (block_n, splits, stages) by scripts/tune_gemm.py
+if os.path.exists(TUNE_PATH):
+    try:
+        with open(TUNE_PATH) as _f:
+            TUNE_TABLE = {k: tuple(v) for k, v in json.load(_f).get("table", {}).items()}
+    except Exception:  # a corrupt table only costs performance
+        TUNE_TABLE = {}
+
+
+def gemm_key(d: Gemm) -> str:
+    kb = sum(d.g[i].ntaps * (d.g[i].k_per_tap // 64) for i in range(d.ngroups)) * d.npass
+    return f"{d.conv}:{d.m}:{d.n}:{kb}:{d.epi}"
+
+
 def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
     L = lib()
+    if d.block_n == 0 and d.splits == 0:
+        key = gemm_key(d)
+        if TUNER is not None and key not in TUNE_TABLE:
+            TUNE_TABLE[key] = TUNER(d, ws or default_workspace(), key)
+        t = TUNE_TABLE.get(key)
+        if t is not None:
+            d.block_n, d.splits, d.stages = t
     need = L.dfu_gemm_workspace(C.byref(d))
     if need:
         ws = ws or default_workspace()
         buf = ws.ensure(need)
         d.workspace = buf.data_ptr()
         d.workspace_bytes = buf.numel()
-        d.tile_counters = ws.counters.data_ptr()
-        d.tile_counters_len = ws.counters.numel()
     k = sum(d.g[i].ntaps * d.g[i].k_per_tap for i in range(d.ngroups))
-    with _Prof("gemm_conv" if d.conv else "gemm_linear", 1, 2.0 * d.m * d.n * k):
+    with _Prof("gemm_conv" if d.conv else "gemm_linear", 2 if need else 1, 2.0 * d.m * d.n * k):
         check(L.dfu_gemm(C.byref(d), _stream()), "dfu_gemm")
 
 

@@ -99,11 +99,11 @@ typedef struct DfuGemm {
   int32_t stages;
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
   size_t workspace_bytes;
-  int32_t* tile_counters;  /* split-K arrival counters, one per output tile: ZERO on entry, left zero on exit */
-  int32_t tile_counters_len;
 } DfuGemm;
 
 int dfu_gemm(const DfuGemm* desc, void* stream);
+/* The tiling dfu_gemm would choose: out[6] = {block_n, splits, stages, tiles_m, tiles_n, k_blocks}. No GPU needed. */
+int dfu_gemm_plan(const DfuGemm* desc, int32_t* out);
 /* Workspace bytes dfu_gemm needs for this descriptor with automatic tiling (0 if none). */
 size_t dfu_gemm_workspace(const DfuGemm* desc);
 

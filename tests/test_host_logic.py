@@ -19,7 +19,8 @@ def test_library_exports_every_header_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"{n} declared in the header but not exported"
-    bound = set(_lib.SIGNATURES) | {"dfu_version", "dfu_last_error", "dfu_num_sms", "dfu_gemm", "dfu_gemm_workspace"}
+    bound = set(_lib.SIGNATURES) | {"dfu_version", "dfu_last_error", "dfu_num_sms", "dfu_gemm", "dfu_gemm_workspace",
+                                     "dfu_gemm_plan"}
     assert set(names) == bound, set(names) ^ bound
     assert L.dfu_version() >= 100
 
@@ -47,12 +48,12 @@ def test_struct_layout_matches_header(tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "diffute_b200.h"\n'
                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(DfuGemmOperand), sizeof(DfuGemm), '
                    'offsetof(DfuGemmOperand,b), offsetof(DfuGemmOperand,tap_dn), offsetof(DfuGemm,g), '
-                   'offsetof(DfuGemm,conv), offsetof(DfuGemm,tile_counters));return 0;}')
+                   'offsetof(DfuGemm,conv), offsetof(DfuGemm,workspace));return 0;}')
     exe = tmp_path / "lay"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.GemmOperand), C.sizeof(_lib.Gemm), _lib.GemmOperand.b.offset, _lib.GemmOperand.tap_dn.offset,
-            _lib.Gemm.g.offset, _lib.Gemm.conv.offset, _lib.Gemm.tile_counters.offset]
+            _lib.Gemm.g.offset, _lib.Gemm.conv.offset, _lib.Gemm.workspace.offset]
     assert got == want, (got, want)
 
 
