@@ -90,6 +90,17 @@ __device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, f
   return v;
 }
 
+// residual already fetched by the caller (t = 0 when there is none)
+__device__ __forceinline__ void epi_quad_res(const EpiParams& e, int m, int n, float4 v, float4 t) {
+  v = epi_affine(e, m, n, v);
+  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  if (e.epi == DFU_EPI_F32) {
+    *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;
+  } else {
+    store_f16x4(e.out_f16 + static_cast<size_t>(m) * e.ldh + n, v, e.out_planes > 1, e.out_plane_stride);
+  }
+}
+
 __device__ __forceinline__ void epi_quad(const EpiParams& e, int m, int n, float4 v) {
   v = epi_affine(e, m, n, v);
   if (e.residual) {
@@ -294,17 +305,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (vr) epi_geglu_quad(p.e, mr, n + cq * 4, a, g);
         }
       } else {
+        // all 8 rows' residual quads are requested before any is consumed: one memory latency per chunk, not eight
+        int mrs[8];
+        float4 res[8];
+        const bool has_res = (p.splits == 1) && (p.e.residual != nullptr);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3);
+          const int mr = __shfl_sync(0xffffffffu, m, row);
+          const int vr = __shfl_sync(0xffffffffu, vmask, row);
+          mrs[it] = vr ? mr : -1;
+          res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && vr)
+            res[it] = *reinterpret_cast<const float4*>(p.e.residual + static_cast<size_t>(mr) * p.e.ldr + n + (lane & 7) * 4);
+        }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3), cq = lane & 7;
-          const int mr = __shfl_sync(0xffffffffu, m, row);
-          const int vr = __shfl_sync(0xffffffffu, vmask, row);
           const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
-          if (vr) {
+          if (mrs[it] >= 0) {
             if (p.splits > 1)
-              __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mr) * p.e.N + n + cq * 4), v);
+              __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mrs[it]) * p.e.N + n + cq * 4), v);
             else
-              epi_quad(p.e, mr, n + cq * 4, v);
+              epi_quad_res(p.e, mrs[it], n + cq * 4, v, res[it]);
           }
         }
       }

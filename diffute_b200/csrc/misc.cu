@@ -135,10 +135,17 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
     const float b0 = bias ? bias[co] : 0.f;
 #pragma unroll
     for (int j = 0; j < kSmallInPix; ++j) acc[j] = b0;
-    for (int k = 0; k < K; ++k) {
-      const float wv = __ldg(wt + static_cast<size_t>(k) * Cout + co);
+    for (int k0 = 0; k0 < K; k0 += 9) {  // weights fetched nine at a time: one L2 latency per tap group, not per tap
+      float wv[9];
 #pragma unroll
-      for (int j = 0; j < kSmallInPix; ++j) acc[j] += wv * sm[j * K + k];
+      for (int u = 0; u < 9; ++u) wv[u] = (k0 + u < K) ? __ldg(wt + static_cast<size_t>(k0 + u) * Cout + co) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 9; ++u) {
+        if (k0 + u < K) {
+#pragma unroll
+          for (int j = 0; j < kSmallInPix; ++j) acc[j] += wv[u] * sm[j * K + k0 + u];
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < kSmallInPix; ++j)

@@ -156,8 +156,18 @@ __global__ void gn_apply_kernel(GnApply a) {
     const int g = tid >> 3, sub = tid & 7;
     if (g < a.groups) {
       double sum = 0.0, sq = 0.0;
-      for (int k = sub; k < a.nchunks; k += 8) {
-        const float2 t = a.partial[(static_cast<size_t>(b) * a.nchunks + k) * a.groups + g];
+      const float2* pp = a.partial + static_cast<size_t>(b) * a.nchunks * a.groups + g;
+      int k = sub;
+      for (; k + 24 < a.nchunks; k += 32) {  // four independent loads in flight per thread, fixed summation order
+        const float2 t0 = pp[static_cast<size_t>(k) * a.groups];
+        const float2 t1 = pp[static_cast<size_t>(k + 8) * a.groups];
+        const float2 t2 = pp[static_cast<size_t>(k + 16) * a.groups];
+        const float2 t3 = pp[static_cast<size_t>(k + 24) * a.groups];
+        sum = (((sum + t0.x) + t1.x) + t2.x) + t3.x;
+        sq = (((sq + t0.y) + t1.y) + t2.y) + t3.y;
+      }
+      for (; k < a.nchunks; k += 8) {
+        const float2 t = pp[static_cast<size_t>(k) * a.groups];
         sum += t.x;
         sq += t.y;
       }
