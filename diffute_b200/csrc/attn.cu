@@ -4,13 +4,16 @@
 // 577 glyph tokens) in BasicTransformerBlock — SURVEY.md A.1, reached from app.ipynb:814.
 //
 // One CTA = 128 query rows of one (sample, head); it streams K/V in blocks of 128 keys:
-//   warps 0-3 : softmax warpgroup; thread r owns query row r (= TMEM lane r): row max / sum need no shuffles.
+//   warps 0-7 : two softmax warpgroups.  Thread (wg, r) owns query row r (= TMEM lane r) for the 64 key columns
+//               [64*wg, 64*wg+64) of each S block and the 32 output columns [32*wg, 32*wg+32) of O: the exp / convert
+//               work per block — the binding resource of this kernel (MUFU + issue slots) — is spread over 8 warps.
+//               The two threads of a row exchange their partial row max through shared memory once per block.
 //               S is read from TMEM with tcgen05.ld, P is written to shared memory as fp16 (hi [, lo]) in the
 //               128-byte-swizzled K-major layout the next MMA consumes; O is accumulated in registers with the
 //               online-softmax rescale.
-//   warp 4    : TMA producer (Q once; K and V double-buffered rings; 4-D maps so rows past the sequence end are
+//   warp 8    : TMA producer (Q once; K and V double-buffered rings; 4-D maps so rows past the sequence end are
 //               zero-filled per sample and per plane).
-//   warp 5    : tcgen05.mma issuer: S = Q K^T (K-major B), then O_blk = P V with V consumed MN-major straight
+//   warp 9    : tcgen05.mma issuer: S = Q K^T (K-major B), then O_blk = P V with V consumed MN-major straight
 //               from its natural [key, d] layout (no transpose pass).
 // In FP16X2 mode both contractions run as three passes over (hi, lo) operand planes.
 #include "common.cuh"
@@ -18,7 +21,8 @@
 
 namespace dfu {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
+constexpr int kSoftmaxThreads = 256;
 constexpr int kBQ = 128;    // queries per CTA
 constexpr int kBKV = 128;   // keys per block
 constexpr int kD = 64;
@@ -40,7 +44,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   pdl_trigger();
@@ -73,7 +77,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = blockIdx.z;
   const int nblk = (p.Nk + kBKV - 1) / kBKV;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -85,13 +89,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(&s_full, 1);
-    mbar_init(&s_free, 128);
-    mbar_init(&p_full, 128);
+    mbar_init(&s_free, kSoftmaxThreads);
+    mbar_init(&p_full, kSoftmaxThreads);
     mbar_init(&o_full, 1);
-    mbar_init(&o_free, 128);
+    mbar_init(&o_free, kSoftmaxThreads);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(&tmem_base_smem, 256);
     tmem_relinquish();
   }
@@ -101,9 +105,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_S = tmem_base;        // 128 columns
   const uint32_t tmem_O = tmem_base + 128;  // 64 columns
+  const uint32_t tmem_X = tmem_base + 192;  // 4 spare columns: per-row exchange between the two softmax warpgroups
   pdl_wait();
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===== TMA producer ======================================================================
     if (lane == 0) {
       mbar_arrive_expect_tx(&q_full, planes * kTile);
@@ -122,7 +127,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, j * kBKV, b, pl);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===== MMA issuer ========================================================================
     if (lane == 0) {
       const uint32_t idesc_qk = umma_idesc_f16(128, kBKV, 0);
@@ -174,28 +179,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // ===== softmax warpgroup (warps 0..3) ======================================================
-    const int r = threadIdx.x;  // query row within the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // ===== softmax warpgroups (warps 0..7) ======================================================
+    const int wg = warp >> 2;          // 0: key columns 0..63 / O columns 0..31; 1: the other halves
+    const int r = threadIdx.x & 127;   // query row within the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-    float acc[kD];
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     const float c2 = p.scale_log2;
     const uint32_t prow = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
+    uint8_t* tile_hi = sP + wg * kTile + prow;        // this warpgroup's 64 keys are exactly P tile `wg`
+    uint8_t* tile_lo = sP + (2 + wg) * kTile + prow;
 
     auto accumulate_o = [&](int j) {
       mbar_wait(&o_full, j & 1);
       tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld32(tmem_O + lane_off + wg * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_O + lane_off + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * alpha_prev + __uint_as_float(raw[i]);
-      }
+      for (int i = 0; i < 32; ++i) acc[i] = acc[i] * alpha_prev + __uint_as_float(raw[i]);
       tc_fence_before();
       mbar_arrive(&o_free);
     };
@@ -203,33 +208,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
-      const int kv_valid = p.Nk - j * kBKV;  // columns >= kv_valid are padding
-      // pass 1: row max
-      float mx = m;
+      const int kv_valid = p.Nk - j * kBKV - wg * 64;  // own columns >= kv_valid are padding
+      const bool full = kv_valid >= 64;                 // warp-uniform: interior blocks skip the tail predicates
+      // pass 1: max over the own 64 columns, then combine with the partner thread of the row
+      float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float v = (c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
+          const float v = (full || c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
           mx = fmaxf(mx, v);
         }
       }
+      // exchange through two spare TMEM columns of the row's own lane (double-buffered by block parity): no shared
+      // memory, so two CTAs still fit one SM
+      const uint32_t xs = tmem_X + lane_off + (j & 1) * 2;
+      tmem_st1(xs + wg, __float_as_uint(mx));
+      tmem_st_wait();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_fence_after();
+      const float other = __uint_as_float(tmem_ld1(xs + (wg ^ 1)));
+      tmem_ld_wait();
+      mx = fmaxf(m, fmaxf(mx, other));
       const float alpha = fast_exp2((m - mx) * c2);  // first block: exp2(-inf) = 0
       // the previous block's P*V must be finished before P is overwritten; fold its result in now
       if (j > 0) accumulate_o(j - 1);
-      // pass 2: probabilities -> shared memory (swizzled K-major fp16), row sum
+      // pass 2: probabilities -> shared memory (swizzled K-major fp16), partial row sum
       const float mc = mx * c2;
       float rowsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
         tmem_ld_wait();
-        uint8_t* tile_hi = sP + (c >> 1) * kTile + prow;
-        uint8_t* tile_lo = sP + (2 + (c >> 1)) * kTile + prow;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {  // 16-byte units of 8 probabilities
           float pv[8];
@@ -237,13 +252,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 8; ++i) {
             const int col = c * 32 + u * 8 + i;
             const float e = fast_exp2(__uint_as_float(raw[u * 8 + i]) * c2 - mc);
-            pv[i] = (col < kv_valid) ? e : 0.f;
+            pv[i] = (full || col < kv_valid) ? e : 0.f;
             rowsum += pv[i];
           }
           __align__(16) __half2 h[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
-          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u);
+          const uint32_t unit = static_cast<uint32_t>(c * 4 + u);
           const uint32_t off = (unit ^ sw) << 4;
           *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
           if (planes == 2) {
@@ -261,17 +276,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(&s_free);       // S may be overwritten by the next Q K^T
       fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
       mbar_arrive(&p_full);
-      l = l * alpha + rowsum;
+      l = l * alpha + rowsum;     // partial (own columns); both threads of a row apply the same alpha
       m = mx;
       alpha_prev = alpha;
     }
     accumulate_o(nblk - 1);
+    // total row sum = partial(wg 0) + partial(wg 1), added in that order by both threads
+    {
+      const uint32_t xs = tmem_X + lane_off + (nblk & 1) * 2;
+      tmem_st1(xs + wg, __float_as_uint(l));
+      tmem_st_wait();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_fence_after();
+      const float l0 = __uint_as_float(tmem_ld1(xs));
+      const float l1 = __uint_as_float(tmem_ld1(xs + 1));
+      tmem_ld_wait();
+      l = l0 + l1;
+    }
     const int q = q0 + r;
     if (q < p.Nq) {
       const float inv = 1.0f / l;
-      __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD;
+      __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + wg * 32;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         __align__(16) __half2 h[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(acc[u * 8 + 2 * i] * inv, acc[u * 8 + 2 * i + 1] * inv);
@@ -291,7 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -333,7 +361,7 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 128;
   static bool attr = false;
   if (!attr) {
-    DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   dim3 grid((Nq + kBQ - 1) / kBQ, heads, B);
