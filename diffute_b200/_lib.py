@@ -37,7 +37,7 @@ class Gemm(C.Structure):
         ("out_f32", C.c_void_p), ("ldo", C.c_int32),
         ("out_f16", C.c_void_p), ("ldh", C.c_int32), ("out_planes", C.c_int32), ("out_plane_stride", C.c_int64),
         ("block_n", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("sync_words", C.c_void_p),
     ]
 
 
@@ -82,7 +82,8 @@ def _declare_rest(L):
 _vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 SIGNATURES = {
     "dfu_groupnorm_workspace": (_sz, [_i, _i, _i, _i]),
-    "dfu_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dfu_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp,
+                           _vp]),
     "dfu_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _i, _i64, _vp]),
     "dfu_cast_f16": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     "dfu_timestep_embedding": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),

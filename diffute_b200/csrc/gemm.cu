@@ -53,6 +53,7 @@ struct GemmKernelParams {
   uint32_t b_tx_bytes;
   uint32_t tmem_cols;
   float* ws;
+  unsigned int* sync;  // grid-barrier words (zero between launches); non-null => fused split-K second stage
   EpiParams e;
 };
 
@@ -126,7 +127,45 @@ __device__ __forceinline__ void epi_geglu_quad(const EpiParams& e, int m, int n_
 
 constexpr int kStageLd = 36;                          // floats per staged row (16-byte aligned, conflict-free)
 constexpr int kStageFloats = 32 * kStageLd;           // per epilogue warp
-constexpr uint32_t kStageBytes = 4 * kStageFloats * 4;
+
+// split-K second stage: every thread owns one output quad, sums the `splits` fp32 partials in slice order
+// (deterministic), four independent 16-byte loads in flight at a time, then runs the fused epilogue.
+__device__ __forceinline__ float4 sum_partials(const float* __restrict__ src, size_t plane, int splits) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + (s + 0) * plane));
+    const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + (s + 1) * plane));
+    const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + (s + 2) * plane));
+    const float4 t3 = __ldcg(reinterpret_cast<const float4*>(src + (s + 3) * plane));
+    v.x = (((v.x + t0.x) + t1.x) + t2.x) + t3.x;
+    v.y = (((v.y + t0.y) + t1.y) + t2.y) + t3.y;
+    v.z = (((v.z + t0.z) + t1.z) + t2.z) + t3.z;
+    v.w = (((v.w + t0.w) + t1.w) + t2.w) + t3.w;
+  }
+  for (; s < splits; ++s) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + s * plane));
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  }
+  return v;
+}
+
+// one output quad of the split-K second stage: sum the partials in slice order, then the fused epilogue
+__device__ __forceinline__ void reduce_quad(const float* __restrict__ ws, int splits, const EpiParams& e, long long idx) {
+  const bool geglu = e.epi == DFU_EPI_GEGLU;
+  const int qpr = geglu ? e.N / 8 : e.N / 4;
+  const size_t plane = static_cast<size_t>(e.M) * e.N;
+  const int m = static_cast<int>(idx / qpr);
+  const int qi = static_cast<int>(idx % qpr);
+  if (geglu) {
+    const int n_a = (qi >> 2) * 32 + (qi & 3) * 4;
+    const float* src = ws + static_cast<size_t>(m) * e.N + n_a;
+    epi_geglu_quad(e, m, n_a, sum_partials(src, plane, splits), sum_partials(src + 16, plane, splits));
+  } else {
+    const int n = qi * 4;
+    epi_quad(e, m, n, sum_partials(ws + static_cast<size_t>(m) * e.N + n, plane, splits));
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -332,6 +371,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
+    if (p.splits > 1 && p.sync != nullptr) {
+      // Fused second stage (all CTAs of this launch are co-resident): once every slice has parked its partial tile
+      // in the L2-resident workspace, the epilogue threads of ALL CTAs share the reduction + fused epilogue, one
+      // output quad at a time — the same arithmetic and order as splitk_reduce_kernel, without a second launch.
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) grid_barrier(p.sync, gridDim.x);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long total = static_cast<long long>(p.e.M) * (p.e.epi == DFU_EPI_GEGLU ? p.e.N / 8 : p.e.N / 4);
+      for (long long idx = static_cast<long long>(blockIdx.x) * 128 + (threadIdx.x - 64); idx < total;
+           idx += static_cast<long long>(gridDim.x) * 128)
+        reduce_quad(p.ws, p.splits, p.e, idx);
+    }
   }
 
   tc_fence_before();
@@ -342,48 +394,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 }
 
-// split-K second stage: every thread owns one output quad, sums the `splits` fp32 partials in slice order
-// (deterministic), four independent 16-byte loads in flight at a time, then runs the fused epilogue.
-__device__ __forceinline__ float4 sum_partials(const float* __restrict__ src, size_t plane, int splits) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  int s = 0;
-  for (; s + 4 <= splits; s += 4) {
-    const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + (s + 0) * plane));
-    const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + (s + 1) * plane));
-    const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + (s + 2) * plane));
-    const float4 t3 = __ldcg(reinterpret_cast<const float4*>(src + (s + 3) * plane));
-    v.x = (((v.x + t0.x) + t1.x) + t2.x) + t3.x;
-    v.y = (((v.y + t0.y) + t1.y) + t2.y) + t3.y;
-    v.z = (((v.z + t0.z) + t1.z) + t2.z) + t3.z;
-    v.w = (((v.w + t0.w) + t1.w) + t2.w) + t3.w;
-  }
-  for (; s < splits; ++s) {
-    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + s * plane));
-    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  }
-  return v;
-}
-
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
   pdl_trigger();
   pdl_wait();
-  const bool geglu = e.epi == DFU_EPI_GEGLU;
-  const int qpr = geglu ? e.N / 8 : e.N / 4;  // quads handled per row
-  const long long total = static_cast<long long>(e.M) * qpr;
-  const size_t plane = static_cast<size_t>(e.M) * e.N;
+  const long long total = static_cast<long long>(e.M) * (e.epi == DFU_EPI_GEGLU ? e.N / 8 : e.N / 4);
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int m = static_cast<int>(idx / qpr);
-    const int qi = static_cast<int>(idx % qpr);
-    if (geglu) {
-      const int n_a = (qi >> 2) * 32 + (qi & 3) * 4;
-      const float* src = ws + static_cast<size_t>(m) * e.N + n_a;
-      epi_geglu_quad(e, m, n_a, sum_partials(src, plane, splits), sum_partials(src + 16, plane, splits));
-    } else {
-      const int n = qi * 4;
-      epi_quad(e, m, n, sum_partials(ws + static_cast<size_t>(m) * e.N + n, plane, splits));
-    }
-  }
+       idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    reduce_quad(ws, splits, e, idx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -607,9 +624,18 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
+  p.sync = nullptr;
+  if (pl.splits > 1 && d->sync_words) {
+    int per_sm = 0;
+    DFU_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_tc_kernel, kGemmThreads, pl.smem_bytes));
+    const int tmem_limit = 512 / static_cast<int>(p.tmem_cols);
+    if (per_sm > tmem_limit) per_sm = tmem_limit;
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    if (grid <= per_sm * sms) p.sync = reinterpret_cast<unsigned int*>(d->sync_words);
+  }
   DFU_CHECK_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, mA[0], mB[0], mA[1], mB[1], p));
   DFU_CHECK_CUDA(cudaGetLastError());
-  if (pl.splits > 1) {
+  if (pl.splits > 1 && p.sync == nullptr) {
     const long long total = static_cast<long long>(d->m) * (d->n / (d->epi == DFU_EPI_GEGLU ? 8 : 4));
     long long blocks = (total + 255) / 256;
     const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;

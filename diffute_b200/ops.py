@@ -133,6 +133,8 @@ class Workspace:
         self.device = device
         self.generation = 0  # bumped on every reallocation: captured CUDA graphs holding the old address are stale
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+        # grid-barrier words (GEMM: [0:2], GroupNorm: [2:4]); zeroed once, every kernel leaves them zero
+        self.sync = torch.zeros(8, dtype=torch.int32, device=device)
 
     def ensure(self, nbytes: int):
         if self.buf.numel() < nbytes:
@@ -211,21 +213,22 @@ def gemm_key(d: Gemm) -> str:
 
 def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
     L = lib()
+    ws = ws or default_workspace()
+    d.sync_words = ws.sync.data_ptr()
     if d.block_n == 0 and d.splits == 0:
         key = gemm_key(d)
         if TUNER is not None and key not in TUNE_TABLE:
-            TUNE_TABLE[key] = TUNER(d, ws or default_workspace(), key)
+            TUNE_TABLE[key] = TUNER(d, ws, key)
         t = TUNE_TABLE.get(key)
         if t is not None:
             d.block_n, d.splits, d.stages = t
     need = L.dfu_gemm_workspace(C.byref(d))
     if need:
-        ws = ws or default_workspace()
         buf = ws.ensure(need)
         d.workspace = buf.data_ptr()
         d.workspace_bytes = buf.numel()
     k = sum(d.g[i].ntaps * d.g[i].k_per_tap for i in range(d.ngroups))
-    with _Prof("gemm_conv" if d.conv else "gemm_linear", 2 if need else 1, 2.0 * d.m * d.n * k):
+    with _Prof("gemm_conv" if d.conv else "gemm_linear", 1, 2.0 * d.m * d.n * k):
         check(L.dfu_gemm(C.byref(d), _stream()), "dfu_gemm")
 
 
@@ -311,7 +314,7 @@ def groupnorm(src0: torch.Tensor, gamma, beta, eps: float, silu: bool, prec: int
     with _Prof('groupnorm', 3, 0.0, float(B * H * W * (C0 + C1)) * (8 + 2 * planes * ((out16 is not None) + (raw16 is not None)) + 4 * (out32 is not None))):
         check(L.dfu_groupnorm(src0.data_ptr(), C0, _ptr(src1), C1, B, H * W, groups, gamma.data_ptr(), beta.data_ptr(),
                               eps, int(silu), _ptr(out16), planes, pstride, _ptr(out32), _ptr(raw16), buf.data_ptr(),
-                              buf.numel(), _stream()), "dfu_groupnorm")
+                              buf.numel(), ws.sync[2:].data_ptr(), _stream()), "dfu_groupnorm")
 
 
 def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: torch.Tensor):

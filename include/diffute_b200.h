@@ -99,6 +99,8 @@ typedef struct DfuGemm {
   int32_t stages;
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
   size_t workspace_bytes;
+  void* sync_words;        /* optional: 2 x uint32, ZERO on entry (left zero): lets a split-K launch whose CTAs are all
+                              co-resident run its second stage in the same kernel behind a grid barrier */
 } DfuGemm;
 
 int dfu_gemm(const DfuGemm* desc, void* stream);
@@ -114,12 +116,14 @@ size_t dfu_gemm_workspace(const DfuGemm* desc);
  * Writes any of: normalised(+SiLU) fp16 operand `out16`, the same in fp32 `out32` (feeds the few-channel
  * fp32 output convs), and `raw16`, the un-normalised cast of the input (operand of the 1x1 conv_shortcut).
  * workspace: dfu_groupnorm_workspace() bytes of per-chunk partial sums (deterministic two-stage reduction).
+ * sync_words: optional 2 x uint32, ZERO on entry (left zero): when the launch fits the GPU in one wave the
+ * statistics, a grid barrier and the apply run as ONE kernel that reads the input once.
  */
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups);
 int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, int groups,
                   const float* gamma, const float* beta, float eps, int silu, void* out16, int planes,
                   int64_t plane_stride, float* out32, void* raw16, void* workspace, size_t workspace_bytes,
-                  void* stream);
+                  void* sync_words, void* stream);
 /* BasicTransformerBlock.norm1/2/3 (LayerNorm, eps 1e-5) over [M, C] tokens -> fp16 operand planes. */
 int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* out16,
                   int planes, int64_t plane_stride, void* stream);

@@ -46,9 +46,9 @@ def tuner(d, ws, key):
             if sp > 1 and kb // sp < 2:
                 continue
             tiles = -(-d.m // 128) * (d.n // bn)
-            if tiles * sp > 1200 or (sp > 1 and tiles * sp > 400):
+            if tiles * sp > 1200 or (sp > 1 and tiles * sp > 296):
                 continue
-            for st in ((3, 5) if bn <= 160 else (4,)):
+            for st in ((3, 4, 6) if bn <= 160 else (3, 4)):
                 cands.append((bn, sp, st))
     best, best_t, res = None, 1e30, []
     need_max = 32 * d.m * d.n * 4

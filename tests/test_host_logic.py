@@ -48,12 +48,12 @@ def test_struct_layout_matches_header(tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "diffute_b200.h"\n'
                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(DfuGemmOperand), sizeof(DfuGemm), '
                    'offsetof(DfuGemmOperand,b), offsetof(DfuGemmOperand,tap_dn), offsetof(DfuGemm,g), '
-                   'offsetof(DfuGemm,conv), offsetof(DfuGemm,workspace));return 0;}')
+                   'offsetof(DfuGemm,conv), offsetof(DfuGemm,sync_words));return 0;}')
     exe = tmp_path / "lay"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.GemmOperand), C.sizeof(_lib.Gemm), _lib.GemmOperand.b.offset, _lib.GemmOperand.tap_dn.offset,
-            _lib.Gemm.g.offset, _lib.Gemm.conv.offset, _lib.Gemm.workspace.offset]
+            _lib.Gemm.g.offset, _lib.Gemm.conv.offset, _lib.Gemm.sync_words.offset]
     assert got == want, (got, want)
 
 
