@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
     L.dfu_num_sms.restype = C.c_int
     L.dfu_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
     L.dfu_gemm.restype = C.c_int
+    L.dfu_gemm_stats.argtypes = [C.POINTER(C.c_int64)]
+    L.dfu_gemm_stats.restype = None
     L.dfu_gemm_plan.argtypes = [C.POINTER(Gemm), C.POINTER(C.c_int32)]
     L.dfu_gemm_plan.restype = C.c_int
     L.dfu_gemm_workspace.argtypes = [C.POINTER(Gemm)]

@@ -9,6 +9,7 @@
 // Operands live in shared memory in the 128-byte-swizzled K-major layout that TMA writes and the UMMA
 // descriptors read; a `stages`-deep full/empty mbarrier ring connects producer and issuer.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -538,6 +539,9 @@ static int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& p
   return make_tmap_f16(mB, o.b, 2, bdims, bstr, bbox);
 }
 
+static long long g_stats[6] = {0, 0, 0, 0, 0, 0};  // launches, split launches, fused second stages, reduce launches,
+                                                  // last per_sm, last grid
+
 static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   Plan pl;
   int rc = plan_gemm(d, &pl);
@@ -625,14 +629,21 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
   p.sync = nullptr;
-  if (pl.splits > 1 && d->sync_words) {
+  static const bool fused_ok = !(getenv("DFU_SPLITK_FUSED") && getenv("DFU_SPLITK_FUSED")[0] == '0');
+  if (pl.splits > 1 && d->sync_words && fused_ok) {
     int per_sm = 0;
     DFU_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_tc_kernel, kGemmThreads, pl.smem_bytes));
     const int tmem_limit = 512 / static_cast<int>(p.tmem_cols);
     if (per_sm > tmem_limit) per_sm = tmem_limit;
     const int sms = num_sms() > 0 ? num_sms() : 148;
     if (grid <= per_sm * sms) p.sync = reinterpret_cast<unsigned int*>(d->sync_words);
+    g_stats[4] = per_sm;
+    g_stats[5] = grid;
   }
+  g_stats[0]++;
+  if (pl.splits > 1) g_stats[1]++;
+  if (p.sync) g_stats[2]++;
+  if (pl.splits > 1 && !p.sync) g_stats[3]++;
   DFU_CHECK_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, mA[0], mB[0], mA[1], mB[1], p));
   DFU_CHECK_CUDA(cudaGetLastError());
   if (pl.splits > 1 && p.sync == nullptr) {
@@ -654,6 +665,9 @@ int dfu_gemm(const DfuGemm* desc, void* stream) {
     return DFU_ERR_INVALID;
   }
   return dfu::run_gemm(desc, static_cast<cudaStream_t>(stream));
+}
+void dfu_gemm_stats(int64_t* out) {
+  for (int i = 0; i < 6; ++i) out[i] = dfu::g_stats[i];
 }
 int dfu_gemm_plan(const DfuGemm* desc, int32_t* out) {
   dfu::Plan pl;

@@ -4,6 +4,8 @@
 // the 16-bit (hi / lo) operand planes the tcgen05 contraction core consumes, so the fp32 -> fp16 cast, the
 // activation, the skip concat, the nearest-2x upsample and the stride-2 space-to-depth split never cost a pass
 // of their own.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -499,7 +501,8 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};
   const size_t stats_smem = static_cast<size_t>(ty) * 2 * C * sizeof(float);
-  if (sync_words) {
+  static const bool fused_ok = !(getenv("DFU_GN_FUSED") && getenv("DFU_GN_FUSED")[0] == '0');
+  if (sync_words && fused_ok) {
     // one launch, one read of the input, when the whole grid is co-resident: pick the fewest pixels per thread
     // (most CTAs) that still fits the GPU in one wave
     GnApply f;

@@ -232,6 +232,13 @@ def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
         check(L.dfu_gemm(C.byref(d), _stream()), "dfu_gemm")
 
 
+def gemm_stats():
+    """{launches, split, fused_second_stage, reduce_launches, last_per_sm, last_grid} since process start."""
+    out = (C.c_int64 * 6)()
+    lib().dfu_gemm_stats(out)
+    return dict(zip(("launches", "split", "fused_second_stage", "reduce_launches", "last_per_sm", "last_grid"), out))
+
+
 def set_epilogue(d: Gemm, *, out_f32=None, out_f16=None, bias=None, rowvec=None, rows_per_sample=0, residual=None,
                  alpha: float = 1.0, geglu: bool = False):
     d.alpha = alpha

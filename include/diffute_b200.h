@@ -106,6 +106,9 @@ typedef struct DfuGemm {
 int dfu_gemm(const DfuGemm* desc, void* stream);
 /* The tiling dfu_gemm would choose: out[6] = {block_n, splits, stages, tiles_m, tiles_n, k_blocks}. No GPU needed. */
 int dfu_gemm_plan(const DfuGemm* desc, int32_t* out);
+/* Process-wide counters: out[6] = {gemm launches, split-K launches, fused second stages, separate reduce launches,
+ * last occupancy per SM, last grid}. */
+void dfu_gemm_stats(int64_t* out);
 /* Workspace bytes dfu_gemm needs for this descriptor with automatic tiling (0 if none). */
 size_t dfu_gemm_workspace(const DfuGemm* desc);
 

@@ -34,4 +34,8 @@ for (M, N, K, tune) in [(4096, 320, 320, (0, 0, 0)), (1024, 640, 640, (0, 0, 0))
     bench(f"linear {M}x{N}x{K} tune={tune}", lambda: ops.linear(a16, w16, N, 1, tune=tune, out_f32=out, bias=bias, residual=res), n=100)
 xg = torch.randn(1, 64, 64, 320, device=dev); gg = torch.ones(320, device=dev); bg = torch.zeros(320, device=dev)
 og = torch.empty(1, 1, 64, 64, 320, dtype=torch.float16, device=dev)
-bench("groupnorm 64x64x320 (2 launches)", lambda: ops.groupnorm(xg, gg, bg, 1e-5, True, 1, out16=og), n=100)
+bench("groupnorm 64x64x320", lambda: ops.groupnorm(xg, gg, bg, 1e-5, True, 1, out16=og), n=100)
+xg2 = torch.randn(1, 16, 16, 1280, device=dev); gg2 = torch.ones(1280, device=dev); bg2 = torch.zeros(1280, device=dev)
+og2 = torch.empty(1, 1, 16, 16, 1280, dtype=torch.float16, device=dev)
+bench("groupnorm 16x16x1280", lambda: ops.groupnorm(xg2, gg2, bg2, 1e-5, True, 1, out16=og2), n=100)
+print(ops.gemm_stats())

@@ -33,4 +33,5 @@ if do_vae:
     pipe.vae.encode(inp["masked_image"].to(dev)); pipe.vae.decode(lat, pre_scale=1 / 0.18215)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("done")
+from diffute_b200 import ops as _o
+print("done", _o.gemm_stats())

@@ -19,21 +19,46 @@ log = {}
 ops.TUNE_TABLE.clear()
 
 
-def time_cfg(d, reps=4):
-    ts = []
-    for i in range(reps + 1):
+NL = 6  # launches per timed window (CUDA events resolve ~2 us: one launch per window cannot rank candidates)
+
+
+def _window(fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ok = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 if ok else None
+
+
+def _flush_only():
+    for _ in range(NL):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = L.dfu_gemm(C.byref(d), torch.cuda.current_stream().cuda_stream)
-        e1.record()
-        if rc != 0:
-            return None
-        torch.cuda.synchronize()
-        if i:
-            ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
-    return ts[len(ts) // 2]
+    return True
+
+
+T_FLUSH = None
+
+
+def time_cfg(d, reps=3):
+    """median over `reps` windows of NL x (L2 flush + launch), minus the flush-only window, per launch"""
+    global T_FLUSH
+    if T_FLUSH is None:
+        _window(_flush_only)
+        T_FLUSH = sorted(_window(_flush_only) for _ in range(5))[2]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        for _ in range(NL):
+            flush.zero_()
+            if L.dfu_gemm(C.byref(d), st) != 0:
+                return False
+        return True
+
+    if _window(run) is None:
+        return None
+    ts = sorted(_window(run) for _ in range(reps))
+    return max((ts[len(ts) // 2] - T_FLUSH) / NL, 0.01)
 
 
 def tuner(d, ws, key):

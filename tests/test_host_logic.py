@@ -20,7 +20,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in the header but not exported"
     bound = set(_lib.SIGNATURES) | {"dfu_version", "dfu_last_error", "dfu_num_sms", "dfu_gemm", "dfu_gemm_workspace",
-                                     "dfu_gemm_plan"}
+                                     "dfu_gemm_plan", "dfu_gemm_stats"}
     assert set(names) == bound, set(names) ^ bound
     assert L.dfu_version() >= 100
 
