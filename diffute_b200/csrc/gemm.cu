@@ -4,8 +4,9 @@
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 2-D for matrices / weights, 4-D NHWC boxes for conv taps;
 //              the halo and the stride-2 / asymmetric padding come from TMA out-of-bounds zero fill)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp32 accumulate in TMEM)
-//   warps 2-5: epilogue, tcgen05.ld TMEM -> registers -> fused bias / time-embedding / residual / GEGLU /
-//              fp16-split stores, 128-bit wide.
+//   warps 2-9: epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks): tcgen05.ld TMEM ->
+//              registers -> smem transpose -> fused bias / time-embedding / residual / GEGLU / fp16-split stores,
+//              coalesced 128-bit wide.
 // Operands live in shared memory in the 128-byte-swizzled K-major layout that TMA writes and the UMMA
 // descriptors read; a `stages`-deep full/empty mbarrier ring connects producer and issuer.
 #include <stdio.h>
@@ -19,7 +20,8 @@ namespace dfu {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KiB smem slot for A (box may fill fewer rows)
 
@@ -297,8 +299,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue warps (2..5) =============================================================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===== epilogue warps (2..9) =============================================================
+    const int q = warp & 3;         // TMEM lane quadrant this warp may access
+    const int cg = (warp - 2) >> 2;  // which half of the 32-column chunks this warp handles
     const int r = q * 32 + lane;
     int m;
     bool valid;
@@ -322,7 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // (the operand ring is idle once tmem_full has fired, so its first 18 KiB double as the staging area)
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * kStageFloats;
     const int vmask = valid ? 1 : 0;
-    for (int c = 0; c < p.block_n; c += 32) {
+    for (int c = cg * 32; c < p.block_n; c += 64) {
       uint32_t raw[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
       tmem_ld_wait();
@@ -377,12 +380,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // in the L2-resident workspace, the epilogue threads of ALL CTAs share the reduction + fused epilogue, one
       // output quad at a time — the same arithmetic and order as splitk_reduce_kernel, without a second launch.
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 64) grid_barrier(p.sync, gridDim.x);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const long long total = static_cast<long long>(p.e.M) * (p.e.epi == DFU_EPI_GEGLU ? p.e.N / 8 : p.e.N / 4);
-      for (long long idx = static_cast<long long>(blockIdx.x) * 128 + (threadIdx.x - 64); idx < total;
-           idx += static_cast<long long>(gridDim.x) * 128)
+      for (long long idx = static_cast<long long>(blockIdx.x) * kEpiThreads + (threadIdx.x - 64); idx < total;
+           idx += static_cast<long long>(gridDim.x) * kEpiThreads)
         reduce_quad(p.ws, p.splits, p.e, idx);
     }
   }
@@ -629,7 +632,9 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
   p.sync = nullptr;
-  static const bool fused_ok = !(getenv("DFU_SPLITK_FUSED") && getenv("DFU_SPLITK_FUSED")[0] == '0');
+  // measured on B200: a grid barrier (~4-5 us) costs more than the second launch it saves (~2.5 us with PDL),
+  // so the fused second stage is opt-in (DFU_SPLITK_FUSED=1)
+  static const bool fused_ok = getenv("DFU_SPLITK_FUSED") && getenv("DFU_SPLITK_FUSED")[0] == '1';
   if (pl.splits > 1 && d->sync_words && fused_ok) {
     int per_sm = 0;
     DFU_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_tc_kernel, kGemmThreads, pl.smem_bytes));

@@ -501,7 +501,9 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};
   const size_t stats_smem = static_cast<size_t>(ty) * 2 * C * sizeof(float);
-  static const bool fused_ok = !(getenv("DFU_GN_FUSED") && getenv("DFU_GN_FUSED")[0] == '0');
+  // measured on B200 (in-graph, 64x64x320): fused 15.9 us vs stats+apply 12.3 us — the grid barrier costs more than
+  // the launch it saves, so the single-launch variant is opt-in (DFU_GN_FUSED=1)
+  static const bool fused_ok = getenv("DFU_GN_FUSED") && getenv("DFU_GN_FUSED")[0] == '1';
   if (sync_words && fused_ok) {
     // one launch, one read of the input, when the whole grid is co-resident: pick the fewest pixels per thread
     // (most CTAs) that still fits the GPU in one wave
