@@ -334,6 +334,10 @@ def run_gpu(args):
                 "image_gflop": IMAGE_GFLOP,
                 "image_frac_of_flop_roofline": (IMAGE_GFLOP / 1e3) * B / (t_res / args.steps) / peaks["tflops"]}
         print(json.dumps(line))
+    import torch.distributed as tdist
+    if tdist.is_initialized():
+        tdist.barrier()
+        tdist.destroy_process_group()
     return 0
 
 

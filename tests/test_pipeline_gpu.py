@@ -113,3 +113,67 @@ def test_sampling_loop_parity(world, up, vp, steps, px, tol):
                  output_type="latent").images
     pipe.scheduler.config["clip_sample"] = False
     assert _rel(lat_f, out.latents.cpu()) < 1e-6
+
+
+def test_config5_768px_cfg_two_steps(world):
+    """BASELINE config 5 shape class: 768x768 (96x96 latent: conv tiles of 96 columns, 9216-token self-attention and
+    d=512 VAE attention) with classifier-free guidance (batch 2B through the UNet, unfused scheduler path)."""
+    from diffute_b200 import synthetic
+    from diffute_b200.pipeline import DiffUTEPipeline
+    from oracle import DDIMOracle, sample_loop
+    usd, vsd, uo, vo = world
+    pipe = DiffUTEPipeline.from_synthetic("fp16x2", "fp16x2", state_dicts=(usd, vsd))
+    inp = synthetic.make_inputs(1, 768, 768)
+    g = torch.Generator().manual_seed(11)
+    neg = torch.randn((1, 577, 1024), generator=g)
+    out = pipe(masked_image=inp["masked_image"], mask_image=inp["mask"], glyph_embeds=inp["glyph_embeds"],
+               negative_glyph_embeds=neg, guidance_scale=2.0, latents=inp["latents"],
+               posterior_noise=inp["posterior_noise"], num_inference_steps=2)
+    ref = sample_loop(uo, vo, DDIMOracle(), inp["masked_image"], inp["mask"], inp["glyph_embeds"], inp["latents"], 2,
+                      posterior_noise=inp["posterior_noise"], guidance_scale=2.0, negative_glyph_embeds=neg)
+    err = _rel(out.images, ref)
+    print(f"768px CFG x2, 2 steps: decoded RGB maxrel {err:.3e}")
+    assert err < 1e-3, err
+
+
+def test_from_pretrained_folder_and_ddpm_reference_path(world, tmp_path):
+    """f1: diffusers folder layout round trip (vae/ + scheduler/), and the sampler the reference actually runs
+    (DDPMScheduler, app.ipynb:545/:816) through the pipeline with a seeded generator."""
+    import json
+    import os
+    from diffute_b200 import arch, checkpoint, synthetic
+    from diffute_b200.pipeline import DiffUTEPipeline
+    from diffute_b200.schedulers import DDPMScheduler
+    from diffute_b200.vae import AutoencoderKL
+    from oracle import DDPMOracle
+    usd, vsd, uo, vo = world
+    checkpoint.save_diffusers_folder(str(tmp_path), "vae", dict(arch.SD2_VAE_CONFIG), vsd, "AutoencoderKL")
+    os.makedirs(tmp_path / "scheduler")
+    json.dump({"_class_name": "PNDMScheduler", **arch.SD2_SCHEDULER_CONFIG, "skip_prk_steps": True},
+              open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    vae = AutoencoderKL.from_pretrained(str(tmp_path), subfolder="vae", precision="fp16x2")
+    assert abs(vae.config.scaling_factor - 0.18215) < 1e-12 and len(vae.config.block_out_channels) == 4
+    inp = synthetic.make_inputs(1, 64, 64)
+    a = vae.encode(inp["image"].cuda()).latent_dist.mode()
+    assert _rel(a, vo.encode(inp["image"]).latent_dist.mode()) < 1e-4
+    sched = DDPMScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
+    pipe = DiffUTEPipeline.from_synthetic("fp16x2", "fp16x2", state_dicts=(usd, vsd))
+    pipe.scheduler = sched
+    out = pipe(masked_image=inp["masked_image"], mask_image=inp["mask"], glyph_embeds=inp["glyph_embeds"],
+               latents=inp["latents"], posterior_noise=inp["posterior_noise"], num_inference_steps=4,
+               generator=torch.Generator().manual_seed(3)).images
+    # oracle loop with the same DDPM noise stream (CPU generator, like app.ipynb:798 + the scheduler's randn)
+    import torch.nn.functional as F
+    o = DDPMOracle()
+    o.set_timesteps(4)
+    gen = torch.Generator().manual_seed(3)
+    mask_l = F.interpolate(inp["mask"], size=(8, 8))
+    ml = vo.encode(inp["masked_image"]).latent_dist.sample(noise=inp["posterior_noise"]) * 0.18215
+    lat = inp["latents"].clone()
+    for t in o.timesteps:
+        eps = uo(torch.cat([lat, mask_l, ml], 1), t, inp["glyph_embeds"]).sample
+        lat = o.step(eps, t, lat, generator=gen).prev_sample
+    ref = vo.decode(lat / 0.18215).sample
+    err = _rel(out, ref)
+    print(f"DDPM 4-step loop (reference sampler): decoded RGB maxrel {err:.3e}")
+    assert err < 1e-3, err
