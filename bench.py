@@ -273,16 +273,37 @@ def run_gpu(args):
     peaks = _peaks()
     passes = 3 if up == "fp16x2" else 1
     gk = [per_kernel.get("gemm_conv", {}), per_kernel.get("gemm_linear", {})]
-    g_ms = sum(k.get("ms_per_step", 0.0) for k in gk)
+    g_ms_events = sum(k.get("ms_per_step", 0.0) for k in gk)
     g_gf = sum(k.get("gflop", 0.0) for k in gk)  # algorithmic: each contraction counted once, whatever the passes
     g_n = sum(k.get("launches", 0) for k in gk)
+
+    # In-graph cost of each kernel class by ablation: replay the captured step with that class's launches removed
+    # (same buffers, same order, PDL edges intact) and take the difference — CUDA events on the replay stream, no
+    # per-launch event overhead.  This is the duration used for the roofline.
+    def graph_ms(ablate):
+        ops.ABLATE = set(ablate)
+        try:
+            pipe.unet._forward_impl(B, h, w, srcs=srcs, t=state[:B])
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                pipe.unet._forward_impl(B, h, w, srcs=srcs, t=state[:B])
+        finally:
+            ops.ABLATE = set()
+        gr.replay()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            gr.replay()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / 20
+
+    full_ms = graph_ms(())
+    in_graph = {c: max(full_ms - graph_ms((c,)), 0.0) for c in ("gemm", "attention", "groupnorm", "layernorm")}
+    g_ms = in_graph["gemm"] if in_graph["gemm"] > 0 else g_ms_events
     achieved = (g_gf / 1e3) / (g_ms / 1e3) if g_ms > 0 else 0.0  # TFLOP/s
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
-    if os.path.exists(tp) and B == 1:
-        with open(tp) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_total"] / tj["gemm_launches_per_unet_step"]  # bytes per launch (ncu capture)
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv + linear)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": traffic, "traffic_note": "avg DRAM bytes per gemm launch over one UNet step (ncu, cold L2): "
@@ -292,10 +313,12 @@ def run_gpu(args):
                 "algorithmic_gflop_per_unet_step": g_gf, "tensor_passes": passes,
                 "unet_step_ms": unet_ms, "unet_step_frac_of_flop_roofline":
                     ((UNET_GFLOP - UNET_CTX_GFLOP) * B / 1e3) / (unet_ms / 1e3) / peaks["tflops"],
-                "per_kernel_ms_per_unet_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items())}}
+                "in_graph_ms_per_unet_step": {k: round(v, 4) for k, v in in_graph.items()},
+                "in_graph_method": "captured step replayed with one kernel class removed; cost = full - ablated",
+                "eager_event_ms_per_unet_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items())}}
     gn = per_kernel.get("groupnorm")
-    if gn and gn["ms_per_step"] > 0:
-        roofline["groupnorm_hbm_gbs"] = gn["gbytes"] / (gn["ms_per_step"] / 1e3)
+    if gn and in_graph["groupnorm"] > 0:
+        roofline["groupnorm_hbm_gbs"] = gn["gbytes"] / (in_graph["groupnorm"] / 1e3)
         roofline["groupnorm_frac_of_hbm"] = roofline["groupnorm_hbm_gbs"] / peaks["hbm"]
 
     total_images = B * world * args.steps

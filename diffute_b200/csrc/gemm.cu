@@ -56,6 +56,7 @@ struct GemmKernelParams {
   uint32_t b_tx_bytes;
   uint32_t tmem_cols;
   float* ws;
+  int cluster;         // > 1: the `splits` K-slices of a tile form a thread-block cluster and reduce through DSMEM
   unsigned int* sync;  // grid-barrier words (zero between launches); non-null => fused split-K second stage
   EpiParams e;
 };
@@ -192,10 +193,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   // ---- tile coordinates -------------------------------------------------------------------
   int bid = blockIdx.x;
-  const int tn = bid % p.tiles_n;
-  bid /= p.tiles_n;
-  const int tm = bid % p.tiles_m;
-  const int split = bid / p.tiles_m;
+  int tn, tm, split;
+  if (p.cluster > 1) {  // the K-slices of one tile are consecutive CTAs = one cluster
+    split = bid % p.cluster;
+    bid /= p.cluster;
+    tn = bid % p.tiles_n;
+    tm = bid / p.tiles_n;
+  } else {
+    tn = bid % p.tiles_n;
+    bid /= p.tiles_n;
+    tm = bid % p.tiles_m;
+    split = bid / p.tiles_m;
+  }
   const int kb0 = static_cast<int>(static_cast<long long>(p.total_kb) * split / p.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(p.total_kb) * (split + 1) / p.splits);
   const int n_tile0 = tn * p.block_n;
@@ -329,6 +338,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t raw[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
       tmem_ld_wait();
+      if (p.cluster > 1) {
+        // cluster split-K: park this slice's fp32 partial tile in OWN shared memory (row r at r * (block_n + 4))
+        float* prow = reinterpret_cast<float*>(smem) + static_cast<size_t>(r) * (p.block_n + 4) + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(prow + 4 * i) =
+              make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                          __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+        continue;
+      }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -388,6 +407,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
            idx += static_cast<long long>(gridDim.x) * kEpiThreads)
         reduce_quad(p.ws, p.splits, p.e, idx);
     }
+  }
+
+  if (p.cluster > 1) {
+    // ---- cluster split-K second stage: every CTA of the cluster reduces 128/S rows of the tile over all S partial
+    // tiles (read through distributed shared memory, slice order => deterministic) and runs the fused epilogue ----
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int S = p.cluster;
+      const int rows_per = kBlockM / S;
+      const bool geglu = p.e.epi == DFU_EPI_GEGLU;
+      const int qpr = geglu ? p.block_n / 8 : p.block_n / 4;
+      const int ldp = p.block_n + 4;
+      const uint32_t part0 = smem_u32(smem);
+      const int te = threadIdx.x - 64;
+      for (int idx = te; idx < rows_per * qpr; idx += kEpiThreads) {
+        const int rr = split * rows_per + idx / qpr;
+        const int qi = idx % qpr;
+        const int col = geglu ? (qi >> 2) * 32 + (qi & 3) * 4 : qi * 4;
+        int m;
+        bool valid;
+        if (p.conv) {
+          const int ix = rr % p.bw;
+          const int t = rr / p.bw;
+          const int iy = t % p.bh;
+          const int in = t / p.bh;
+          const int x = x0 + ix, y = y0 + iy, img = img0 + in;
+          valid = (in < p.bn) && (x < p.W) && (y < p.H) && (img < p.B);
+          m = (img * p.H + y) * p.W + x;
+        } else {
+          m = m0 + rr;
+          valid = m < p.e.M;
+        }
+        if (!valid) continue;
+        const uint32_t loc = part0 + static_cast<uint32_t>(rr * ldp + col) * 4u;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+        for (int q = 0; q < S; ++q) {
+          const uint32_t ra = dsmem_addr(loc, static_cast<uint32_t>(q));
+          const float4 t = ld_dsmem_f4(ra);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+          if (geglu) {
+            const float4 u = ld_dsmem_f4(ra + 64);
+            g.x += u.x; g.y += u.y; g.z += u.z; g.w += u.w;
+          }
+        }
+        if (geglu)
+          epi_geglu_quad(p.e, m, n_tile0 + col, a, g);
+        else
+          epi_quad(p.e, m, n_tile0 + col, a);
+      }
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
   }
 
   tc_fence_before();
@@ -631,11 +701,18 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
+  static const bool cluster_ok = !(getenv("DFU_SPLITK_CLUSTER") && getenv("DFU_SPLITK_CLUSTER")[0] == '0');
+  p.cluster = 0;
+  if (cluster_ok && (pl.splits == 2 || pl.splits == 4 || pl.splits == 8)) {
+    // the partial tile (128 x (block_n + 4) fp32) must fit in the idle operand ring
+    const size_t part = static_cast<size_t>(kBlockM) * (pl.block_n + 4) * 4;
+    if (part <= pl.smem_bytes - 1024) p.cluster = pl.splits;
+  }
   p.sync = nullptr;
   // measured on B200: a grid barrier (~4-5 us) costs more than the second launch it saves (~2.5 us with PDL),
   // so the fused second stage is opt-in (DFU_SPLITK_FUSED=1)
   static const bool fused_ok = getenv("DFU_SPLITK_FUSED") && getenv("DFU_SPLITK_FUSED")[0] == '1';
-  if (pl.splits > 1 && d->sync_words && fused_ok) {
+  if (pl.splits > 1 && !p.cluster && d->sync_words && fused_ok) {
     int per_sm = 0;
     DFU_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_tc_kernel, kGemmThreads, pl.smem_bytes));
     const int tmem_limit = 512 / static_cast<int>(p.tmem_cols);
@@ -648,10 +725,11 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   g_stats[0]++;
   if (pl.splits > 1) g_stats[1]++;
   if (p.sync) g_stats[2]++;
-  if (pl.splits > 1 && !p.sync) g_stats[3]++;
-  DFU_CHECK_CUDA(launch_k(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, mA[0], mB[0], mA[1], mB[1], p));
+  if (pl.splits > 1 && !p.sync && !p.cluster) g_stats[3]++;
+  if (p.cluster) g_stats[2]++;
+  DFU_CHECK_CUDA(launch_kc(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), pl.smem_bytes, stream, p.cluster > 1 ? p.cluster : 1, mA[0], mB[0], mA[1], mB[1], p));
   DFU_CHECK_CUDA(cudaGetLastError());
-  if (pl.splits > 1 && p.sync == nullptr) {
+  if (pl.splits > 1 && p.sync == nullptr && !p.cluster) {
     const long long total = static_cast<long long>(d->m) * (d->n / (d->epi == DFU_EPI_GEGLU ? 8 : 4));
     long long blocks = (total + 255) / 256;
     const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;

@@ -39,20 +39,34 @@ int num_sms();
 // 1 unless DFU_PDL=0: launch with the programmatic-stream-serialization attribute (kernels call pdl_wait()).
 int pdl_enabled();
 
+// cluster_x > 1 launches thread-block clusters of that many consecutive CTAs along x
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                            Args&&... args) {
+inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
-  cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  return launch_kc(kernel, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
 }
 
 }  // namespace dfu

@@ -41,7 +41,11 @@ def _tol(prec, ops):
     (1000, 640, 1024, (128, 1, 4)),      # ragged M
     (64, 1280, 1280, (0, 0, 0)),         # tiny M -> auto split-K
     (577, 640, 1024, (0, 0, 0)),         # glyph-token K/V projection shape
-    (256, 1280, 5120, (256, 2, 4)),
+    (256, 1280, 5120, (256, 2, 4)),      # splits 2/4/8 reduce inside the kernel through a thread-block cluster
+    (256, 1280, 1280, (128, 4, 3)),
+    (64, 1280, 5120, (160, 8, 3)),
+    (300, 640, 2560, (64, 8, 4)),        # ragged M + cluster reduce
+    (256, 1280, 5120, (160, 6, 3)),      # other split counts go through the workspace + reduce kernel
     (128, 32, 64, (32, 1, 2)),           # single k-block
 ])
 def test_linear_f32_epilogue(ops, prec, M, N, K, tune):
@@ -86,15 +90,16 @@ def test_linear_f16_and_geglu_epilogues(ops, prec):
     bg = _rand((8 * C,), 8, 0.1)
     wg16 = ops.pack_linear_weight(wg, planes, geglu=True)
     bgi = ops.geglu_interleave(bg)
-    outg = torch.zeros((planes, M, 4 * C), dtype=torch.float16, device="cuda")
-    ops.linear(a16, wg16, 8 * C, prec, out_f16=outg, bias=bgi, geglu=True)
-    torch.cuda.synchronize()
     wr = wg.to(torch.float16).double() if prec == 1 else ops.split_f16(wg, 2).double().sum(0)
     p = _recombine(a16) @ wr.T + bg.double()
     refg = p[:, :4 * C] * F.gelu(p[:, 4 * C:])
-    gotg = _recombine(outg)
     tol = 1.5e-3 if prec == 1 else ACC_TOL
-    assert ((gotg - refg).abs().max() / refg.abs().max()).item() < tol
+    for tune in ((0, 0, 0), (160, 2, 3), (128, 3, 3)):   # single pass, cluster split-K, workspace split-K
+        outg = torch.zeros((planes, M, 4 * C), dtype=torch.float16, device="cuda")
+        ops.linear(a16, wg16, 8 * C, prec, tune=tune, out_f16=outg, bias=bgi, geglu=True)
+        torch.cuda.synchronize()
+        gotg = _recombine(outg)
+        assert ((gotg - refg).abs().max() / refg.abs().max()).item() < tol, tune
 
 
 def _conv_ref(x_nhwc, w, stride, pad):
@@ -127,14 +132,17 @@ def test_conv3x3_stride1(ops, prec, B, H, W, Cin, Cout):
     x16 = ops.split_f16(x, planes).reshape(planes * B, H, W, Cin)
     w16 = ops.pack_conv_weight(w, planes)
     out = torch.full((B, H, W, Cout), float("nan"), device="cuda")
-    ops.conv(x16, w16, Cout, prec, (B, H, W), ops.taps_3x3_s1(), out_f32=out.view(B * H * W, Cout), bias=bias,
-             rowvec=temb, rows_per_sample=H * W)
-    torch.cuda.synchronize()
     xr = x16.reshape(planes, B, H, W, Cin).double().sum(0)
     wr = ops.split_f16(w, planes).double().sum(0)
     ref = _conv_ref(xr, wr, 1, 1) + bias.double() + temb.double()[:, None, None, :]
-    err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
-    assert err < ACC_TOL, err
+    bn = 160 if Cout % 160 == 0 else (128 if Cout % 128 == 0 else 64)
+    for tune in ((0, 0, 0), (bn, 4, 3)):   # automatic tiling, then a forced 4-way cluster split-K
+        out.fill_(float("nan"))
+        ops.conv(x16, w16, Cout, prec, (B, H, W), ops.taps_3x3_s1(), tune=tune, out_f32=out.view(B * H * W, Cout),
+                 bias=bias, rowvec=temb, rows_per_sample=H * W)
+        torch.cuda.synchronize()
+        err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < ACC_TOL, (tune, err)
 
 
 @pytest.mark.parametrize("prec", [1, 2])
