@@ -304,6 +304,12 @@ def run_gpu(args):
     in_graph = {c: max(full_ms - graph_ms((c,)), 0.0) for c in ("gemm", "attention", "groupnorm", "layernorm")}
     g_ms = in_graph["gemm"] if in_graph["gemm"] > 0 else g_ms_events
     achieved = (g_gf / 1e3) / (g_ms / 1e3) if g_ms > 0 else 0.0  # TFLOP/s
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    if os.path.exists(tp) and B == 1:
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_total"] / tj["gemm_launches_per_unet_step"]  # bytes per launch (ncu capture)
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv + linear)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": traffic, "traffic_note": "avg DRAM bytes per gemm launch over one UNet step (ncu, cold L2): "
