@@ -30,7 +30,9 @@ __device__ __forceinline__ float4 gn_load(const GnSrc& s, int b, int pix, int cq
   return *reinterpret_cast<const float4*>(s.src1 + (static_cast<size_t>(b) * s.HW + pix) * s.C1 + (c - s.C0));
 }
 
-__global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial) {
+__global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial,
+                                unsigned int* __restrict__ counters, float2* __restrict__ stats, double count,
+                                float eps) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];  // [TY][2][C] per-row-of-threads channel sums, reduced in a fixed order (deterministic)
@@ -72,7 +74,51 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
         q += row[C + tid * cpg + i];
       }
     }
-    partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * groups + tid] = make_float2(a, q);
+    __stcg(&partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * groups + tid], make_float2(a, q));
+    __threadfence();
+  }
+  if (counters == nullptr) return;
+  // The LAST chunk of this sample to finish turns the partials into (mean, rstd): no waiting (an arrival counter, not
+  // a barrier), a fixed summation order (deterministic), and the apply kernel starts from 32 ready numbers.
+  __shared__ int s_last;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&counters[b], 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    if (s_last) counters[b] = 0;  // ready for the next launch
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_last) return;
+  const int nchunks = gridDim.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
+    double sum = 0.0, sqd = 0.0;
+    const float2* pp = partial + static_cast<size_t>(b) * nchunks * groups + g;
+    int k = lane;
+    for (; k + 96 < nchunks; k += 128) {
+      const float2 t0 = __ldcg(pp + static_cast<size_t>(k) * groups);
+      const float2 t1 = __ldcg(pp + static_cast<size_t>(k + 32) * groups);
+      const float2 t2 = __ldcg(pp + static_cast<size_t>(k + 64) * groups);
+      const float2 t3 = __ldcg(pp + static_cast<size_t>(k + 96) * groups);
+      sum = (((sum + t0.x) + t1.x) + t2.x) + t3.x;
+      sqd = (((sqd + t0.y) + t1.y) + t2.y) + t3.y;
+    }
+    for (; k < nchunks; k += 32) {
+      const float2 t = __ldcg(pp + static_cast<size_t>(k) * groups);
+      sum += t.x;
+      sqd += t.y;
+    }
+    sum = warp_sum_d(sum);
+    sqd = warp_sum_d(sqd);
+    if (lane == 0) {
+      const double mean = sum / count;
+      double var = sqd / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[b * groups + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + eps)));
+    }
   }
 }
 
@@ -538,8 +584,10 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
     if (r == 0) return DFU_OK;
     if (r < 0) return DFU_ERR_CUDA;
   }
-  DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), static_cast<size_t>(ty) * 2 * C * sizeof(float), stream, s, groups, ppc, static_cast<float2*>(workspace)));
-  DFU_CHECK_CUDA(cudaGetLastError());
+  // statistics; with arrival counters available the last chunk of each sample also finalises (mean, rstd)
+  float2* stats_out = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
+  unsigned int* counters = (sync_words && B <= 48) ? static_cast<unsigned int*>(sync_words) + 8 : nullptr;
+  DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), stats_smem, stream, s, groups, ppc, static_cast<float2*>(workspace), counters, stats_out, static_cast<double>(C / groups) * HW, eps));
   GnApply a;
   a.s = s;
   a.groups = groups;
@@ -547,9 +595,9 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   a.partial = static_cast<const float2*>(workspace);
   a.nchunks = chunks;
   a.count = static_cast<double>(C / groups) * HW;
-  a.stats = nullptr;
+  a.stats = counters ? stats_out : nullptr;
   const bool inline_finalize = chunks <= 256 && static_cast<int>(block.x * block.y) >= 8 * groups;
-  if (!inline_finalize) {
+  if (!counters && !inline_finalize) {
     float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
     DFU_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(groups, B), dim3(256), 0, stream, static_cast<const float2*>(workspace), chunks, groups, a.count, eps, stats));
     a.stats = stats;

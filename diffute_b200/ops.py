@@ -158,7 +158,7 @@ class Workspace:
         self.generation = 0  # bumped on every reallocation: captured CUDA graphs holding the old address are stale
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
         # grid-barrier words (GEMM: [0:2], GroupNorm: [2:4]); zeroed once, every kernel leaves them zero
-        self.sync = torch.zeros(8, dtype=torch.int32, device=device)
+        self.sync = torch.zeros(64, dtype=torch.int32, device=device)  # [0:2] GEMM barrier, [2:4]+[8:56] GroupNorm
 
     def ensure(self, nbytes: int):
         if self.buf.numel() < nbytes:
@@ -345,7 +345,7 @@ def groupnorm(src0: torch.Tensor, gamma, beta, eps: float, silu: bool, prec: int
     with _Prof('groupnorm', 3, 0.0, float(B * H * W * (C0 + C1)) * (8 + 2 * planes * ((out16 is not None) + (raw16 is not None)) + 4 * (out32 is not None))):
         check(L.dfu_groupnorm(src0.data_ptr(), C0, _ptr(src1), C1, B, H * W, groups, gamma.data_ptr(), beta.data_ptr(),
                               eps, int(silu), _ptr(out16), planes, pstride, _ptr(out32), _ptr(raw16), buf.data_ptr(),
-                              buf.numel(), ws.sync[2:].data_ptr(), _stream()), "dfu_groupnorm")
+                              buf.numel(), ws.sync[2:].data_ptr(), _stream()), "dfu_groupnorm")  # counters at sync[10:]
 
 
 def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: torch.Tensor):

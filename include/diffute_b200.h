@@ -119,8 +119,9 @@ size_t dfu_gemm_workspace(const DfuGemm* desc);
  * Writes any of: normalised(+SiLU) fp16 operand `out16`, the same in fp32 `out32` (feeds the few-channel
  * fp32 output convs), and `raw16`, the un-normalised cast of the input (operand of the 1x1 conv_shortcut).
  * workspace: dfu_groupnorm_workspace() bytes of per-chunk partial sums (deterministic two-stage reduction).
- * sync_words: optional 2 x uint32, ZERO on entry (left zero): when the launch fits the GPU in one wave the
- * statistics, a grid barrier and the apply run as ONE kernel that reads the input once.
+ * sync_words: optional (8 + B) x uint32, ZERO on entry (left zero): words [8, 8+B) are per-sample arrival counters
+ * that let the last statistics CTA of a sample finalise (mean, rstd) so the apply kernel starts from ready numbers;
+ * words [0,2) back the opt-in single-launch variant (DFU_GN_FUSED=1).
  */
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups);
 int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, int groups,
