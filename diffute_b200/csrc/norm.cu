@@ -586,7 +586,10 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   }
   // statistics; with arrival counters available the last chunk of each sample also finalises (mean, rstd)
   float2* stats_out = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
-  unsigned int* counters = (sync_words && B <= 48) ? static_cast<unsigned int*>(sync_words) + 8 : nullptr;
+  // measured on B200: letting the last statistics CTA finalise costs more (0.95 vs 0.69 ms of GroupNorm per UNet
+  // step: a serial tail on the critical path) than combining the partials in every apply CTA's prologue -> opt-in
+  static const bool last_cta = getenv("DFU_GN_LASTCTA") && getenv("DFU_GN_LASTCTA")[0] == '1';
+  unsigned int* counters = (last_cta && sync_words && B <= 48) ? static_cast<unsigned int*>(sync_words) + 8 : nullptr;
   DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), stats_smem, stream, s, groups, ppc, static_cast<float2*>(workspace), counters, stats_out, static_cast<double>(C / groups) * HW, eps));
   GnApply a;
   a.s = s;
