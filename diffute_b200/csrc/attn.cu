@@ -36,6 +36,11 @@ struct AttnParams {
   __half* out;      // [planes][B*Nq][ldo], head h at columns h*64
   int ldo;
   long long out_plane_stride;
+  // split-KV (flash-decoding style): blockIdx.z = b * kv_splits + s handles key blocks [s*bps, (s+1)*bps); partial
+  // (unnormalised O, row max, row sum) go to the workspace and attn_merge_kernel combines them
+  int kv_splits, blocks_per_split;
+  float* ws_o;      // [item][128][64] fp32, item = ((b*heads + head)*q_tiles + q_tile)*kv_splits + s
+  float* ws_ml;     // [item][128][2] (m in raw score units, l)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -74,8 +79,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
   const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nblk = (p.Nk + kBKV - 1) / kBKV;
+  const int b = blockIdx.z / p.kv_splits;
+  const int split = blockIdx.z % p.kv_splits;
+  const int nblk_all = (p.Nk + kBKV - 1) / kBKV;
+  const int jb0 = split * p.blocks_per_split;                       // first key block of this CTA
+  const int nblk = min(p.blocks_per_split, nblk_all - jb0);          // >= 1 by construction of kv_splits
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -120,11 +128,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&k_empty[slot], par);
         mbar_arrive_expect_tx(&k_full[slot], planes * kTile);
         for (int pl = 0; pl < planes; ++pl)
-          tma_load_4d(sK + (slot * planes + pl) * kTile, &tmK, &k_full[slot], p.k_col0 + head * kD, j * kBKV, b, pl);
+          tma_load_4d(sK + (slot * planes + pl) * kTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
         mbar_wait(&v_empty[slot], par);
         mbar_arrive_expect_tx(&v_full[slot], planes * kTile);
         for (int pl = 0; pl < planes; ++pl)
-          tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, j * kBKV, b, pl);
+          tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
       }
     }
   } else if (warp == 9) {
@@ -208,7 +216,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
-      const int kv_valid = p.Nk - j * kBKV - wg * 64;  // own columns >= kv_valid are padding
+      const int kv_valid = p.Nk - (jb0 + j) * kBKV - wg * 64;  // own columns >= kv_valid are padding
       const bool full = kv_valid >= 64;                 // warp-uniform: interior blocks skip the tail predicates
       // pass 1: max over the own 64 columns, then combine with the partner thread of the row
       float mx = -INFINITY;
@@ -295,7 +303,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       l = l0 + l1;
     }
     const int q = q0 + r;
-    if (q < p.Nq) {
+    if (p.kv_splits > 1) {
+      const size_t item = ((static_cast<size_t>(b) * p.heads + head) * gridDim.x + blockIdx.x) * p.kv_splits + split;
+      float4* po = reinterpret_cast<float4*>(p.ws_o + (item * 128 + r) * 64 + wg * 32);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) __stcg(po + u, make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]));
+      if (wg == 0) __stcg(reinterpret_cast<float2*>(p.ws_ml + (item * 128 + r) * 2), make_float2(m, l));
+    } else if (q < p.Nq) {
       const float inv = 1.0f / l;
       __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + wg * 32;
 #pragma unroll
@@ -325,6 +339,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// Combine the kv_splits partial results of one (sample, head, query tile): O = sum_s O_s 2^((m_s - M) c2) / sum_s l_s
+// 2^((m_s - M) c2), slices in order (deterministic).  One 4-column quad per thread.
+__global__ void __launch_bounds__(256) attn_merge_kernel(AttnParams p, int q_tiles) {
+  pdl_trigger();
+  pdl_wait();
+  const int tile = blockIdx.x;                 // (b*heads + head)*q_tiles + q_tile
+  const int q_tile = tile % q_tiles;
+  const int bh = tile / q_tiles;
+  const int head = bh % p.heads, b = bh / p.heads;
+  const size_t item0 = static_cast<size_t>(tile) * p.kv_splits;
+  for (int idx = threadIdx.x; idx < 128 * 16; idx += blockDim.x) {
+    const int r = idx >> 4, cq = idx & 15;
+    const int q = q_tile * kBQ + r;
+    if (q >= p.Nq) continue;
+    float M = -INFINITY;
+    for (int s = 0; s < p.kv_splits; ++s) M = fmaxf(M, __ldcg(p.ws_ml + ((item0 + s) * 128 + r) * 2));
+    float L = 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < p.kv_splits; ++s) {
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + ((item0 + s) * 128 + r) * 2));
+      const float w = fast_exp2((ml.x - M) * p.scale_log2);
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(p.ws_o + ((item0 + s) * 128 + r) * 64 + cq * 4));
+      L += ml.y * w;
+      o.x += t.x * w; o.y += t.y * w; o.z += t.z * w; o.w += t.w * w;
+    }
+    const float inv = 1.0f / L;
+    o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+    __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + cq * 4;
+    __align__(8) __half2 h[2];
+    h[0] = __floats2half2_rn(o.x, o.y);
+    h[1] = __floats2half2_rn(o.z, o.w);
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+    if (p.planes == 2) {
+      const float2 a = __half22float2(h[0]), c = __half22float2(h[1]);
+      __align__(8) __half2 lo[2];
+      lo[0] = __floats2half2_rn(o.x - a.x, o.y - a.y);
+      lo[1] = __floats2half2_rn(o.z - c.x, o.w - c.y);
+      *reinterpret_cast<uint2*>(dst + p.out_plane_stride) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
 static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, int planes, long long plane_stride) {
   uint64_t dims[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(N), static_cast<uint64_t>(B),
                       static_cast<uint64_t>(planes)};
@@ -338,10 +394,31 @@ static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, 
 
 using namespace dfu;
 
+static int attn_auto_splits(int B, int heads, int Nq, int Nk) {
+  // One CTA alone on an SM is latency-bound (~2x slower per key block than two interleaved CTAs): when the
+  // (query tile, head) grid cannot put two CTAs on every SM, cut the key range so that it can.
+  const int q_tiles = (Nq + kBQ - 1) / kBQ;
+  const int nblk = (Nk + kBKV - 1) / kBKV;
+  const int ctas = q_tiles * heads * B;
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  if (nblk < 4 || ctas >= 4 * sms) return 1;
+  int s = (4 * sms + ctas - 1) / ctas;
+  if (s > nblk / 2) s = nblk / 2;
+  if (s > 8) s = 8;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" size_t dfu_attention_workspace(int B, int heads, int Nq, int Nk, int kv_splits) {
+  if (kv_splits <= 0) kv_splits = attn_auto_splits(B, heads, Nq, Nk);
+  if (kv_splits <= 1) return 0;
+  const size_t items = static_cast<size_t>(B) * heads * ((Nq + kBQ - 1) / kBQ) * kv_splits;
+  return items * (128 * 64 + 128 * 2) * sizeof(float);
+}
+
 extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, const void* k, int ldk,
                              int k_col0, const void* v, int ldv, int v_col0, int64_t kv_plane_stride, int B, int heads,
                              int Nq, int Nk, int planes, float scale, void* out, int ldo, int64_t out_plane_stride,
-                             void* stream_) {
+                             int kv_splits, void* workspace, size_t workspace_bytes, void* stream_) {
   DFU_REQUIRE(planes == 1 || planes == 2, "attention: planes=%d", planes);
   DFU_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: empty problem");
   DFU_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be x8");
@@ -358,14 +435,35 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   p.out = static_cast<__half*>(out);
   p.ldo = ldo;
   p.out_plane_stride = out_plane_stride;
+  const int nblk_all = (Nk + kBKV - 1) / kBKV;
+  if (kv_splits <= 0) kv_splits = attn_auto_splits(B, heads, Nq, Nk);
+  if (kv_splits > nblk_all) kv_splits = nblk_all;
+  int bps = (nblk_all + kv_splits - 1) / kv_splits;
+  kv_splits = (nblk_all + bps - 1) / bps;  // no empty slices
+  p.kv_splits = kv_splits;
+  p.blocks_per_split = bps;
+  p.ws_o = nullptr;
+  p.ws_ml = nullptr;
+  const int q_tiles = (Nq + kBQ - 1) / kBQ;
+  if (kv_splits > 1) {
+    const size_t items = static_cast<size_t>(B) * heads * q_tiles * kv_splits;
+    const size_t need = items * (128 * 64 + 128 * 2) * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("attention: split-KV needs %zu workspace bytes, got %zu", need, workspace_bytes);
+      return DFU_ERR_WORKSPACE;
+    }
+    p.ws_o = static_cast<float*>(workspace);
+    p.ws_ml = p.ws_o + items * 128 * 64;
+  }
   const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 128;
   static bool attr = false;
   if (!attr) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  dim3 grid((Nq + kBQ - 1) / kBQ, heads, B);
+  dim3 grid(q_tiles, heads, B * kv_splits);
   DFU_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream_), mQ, mK, mV, p));
-  DFU_CHECK_CUDA(cudaGetLastError());
+  if (kv_splits > 1)
+    DFU_CHECK_CUDA(launch_k(attn_merge_kernel, dim3(B * heads * q_tiles), dim3(256), 0, static_cast<cudaStream_t>(stream_), p, q_tiles));
   return DFU_OK;
 }

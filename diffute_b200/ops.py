@@ -456,14 +456,23 @@ def transpose_f16(x16: torch.Tensor, out16: torch.Tensor):
 
 
 def attention(q16: torch.Tensor, q_col0: int, k16: torch.Tensor, k_col0: int, v16: torch.Tensor, v_col0: int,
-              B: int, heads: int, Nq: int, Nk: int, scale: float, out16: torch.Tensor):
+              B: int, heads: int, Nq: int, Nk: int, scale: float, out16: torch.Tensor, kv_splits: int = 0,
+              ws: Optional[Workspace] = None):
     """q16 [planes, B*Nq, ldq], k16/v16 [planes, B*Nk, ld] fp16 operands (k16 and v16 share the plane stride);
-    out16 [planes, B*Nq, heads*64]."""
+    out16 [planes, B*Nq, heads*64].  kv_splits = 0 lets the library decide (split-KV + merge for under-filled grids)."""
     planes = q16.shape[0]
-    with _Prof('attention', 1, 4.0 * B * heads * Nq * Nk * 64):
-        check(lib().dfu_attention(q16.data_ptr(), q16.stride(1), q_col0, q16.stride(0), k16.data_ptr(), k16.stride(1),
-                                  k_col0, v16.data_ptr(), v16.stride(1), v_col0, k16.stride(0), B, heads, Nq, Nk, planes,
-                                  scale, out16.data_ptr(), out16.stride(1), out16.stride(0), _stream()), "dfu_attention")
+    L = lib()
+    need = L.dfu_attention_workspace(B, heads, Nq, Nk, kv_splits)
+    wptr, wbytes = None, 0
+    if need:
+        ws = ws or default_workspace()
+        buf = ws.ensure(need)
+        wptr, wbytes = buf.data_ptr(), buf.numel()
+    with _Prof('attention', 2 if need else 1, 4.0 * B * heads * Nq * Nk * 64):
+        check(L.dfu_attention(q16.data_ptr(), q16.stride(1), q_col0, q16.stride(0), k16.data_ptr(), k16.stride(1),
+                              k_col0, v16.data_ptr(), v16.stride(1), v_col0, k16.stride(0), B, heads, Nq, Nk, planes,
+                              scale, out16.data_ptr(), out16.stride(1), out16.stride(0), kv_splits, wptr, wbytes,
+                              _stream()), "dfu_attention")
 
 
 def scheduler_step(x, m, noise, a0, a1, p0, d0, d1, sn, clip: bool, y, x0_out=None):

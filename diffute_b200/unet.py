@@ -279,7 +279,7 @@ class UNet2DConditionModel:
         qkv = self._op16("qkv", (M, 3 * C))
         ops.linear(ln, w[b + ".attn1.qkv.w16"], 3 * C, prec, ws=self.ws, out_f16=qkv)
         at = self._op16("attn", (M, C))
-        ops.attention(qkv, 0, qkv, C, qkv, 2 * C, B, heads, N, N, 0.125, at)
+        ops.attention(qkv, 0, qkv, C, qkv, 2 * C, B, heads, N, N, 0.125, at, ws=self.ws)
         t1 = A.get("tok1", (M, C))
         ops.linear(at, w[b + ".attn1.to_out.0.w16"], C, prec, ws=self.ws, out_f32=t1, bias=w[b + ".attn1.to_out.0.b"],
                    residual=t0)
@@ -287,7 +287,7 @@ class UNet2DConditionModel:
         ops.layernorm(t1, w[b + ".norm2.g"], w[b + ".norm2.be"], 1e-5, ln)
         q = self._op16("qkv", (M, C))
         ops.linear(ln, w[b + ".attn2.to_q.w16"], C, prec, ws=self.ws, out_f16=q)
-        ops.attention(q, 0, ctx_kv, 0, ctx_kv, C, B, heads, N, n_ctx, 0.125, at)
+        ops.attention(q, 0, ctx_kv, 0, ctx_kv, C, B, heads, N, n_ctx, 0.125, at, ws=self.ws)
         t2 = A.get("tok0", (M, C))
         ops.linear(at, w[b + ".attn2.to_out.0.w16"], C, prec, ws=self.ws, out_f32=t2, bias=w[b + ".attn2.to_out.0.b"],
                    residual=t1)

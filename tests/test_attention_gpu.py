@@ -44,6 +44,14 @@ def test_attention(ops, planes, B, heads, Nq, Nk, fused):
     out16 = torch.zeros((planes, B * Nq, C), dtype=torch.float16, device="cuda")
     ops.attention(q16, cols[0], k16, cols[1], v16, cols[2], B, heads, Nq, Nk, scale, out16)
     torch.cuda.synchronize()
+    # forced split-KV (2 and 3 key slices + merge kernel) must agree with the automatic choice
+    if Nk > 256:
+        for ks in (2, 3):
+            o2 = torch.zeros_like(out16)
+            ops.attention(q16, cols[0], k16, cols[1], v16, cols[2], B, heads, Nq, Nk, scale, o2, kv_splits=ks)
+            torch.cuda.synchronize()
+            d = (o2.double().sum(0) - out16.double().sum(0)).abs().max().item()
+            assert d < (2e-3 if planes == 1 else 2e-5) * out16.double().sum(0).abs().max().item(), (ks, d)
     qd = q16.double().sum(0)[:, cols[0]:cols[0] + C].reshape(B, Nq, heads, 64).permute(0, 2, 1, 3)
     kd = k16.double().sum(0)[:, cols[1]:cols[1] + C].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
     vd = v16.double().sum(0)[:, cols[2]:cols[2] + C].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
