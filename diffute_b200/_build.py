@@ -30,19 +30,28 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    dig = _digest()
+TRACE_LIB = os.path.join(HERE, "libdiffute_b200_trace.so")
+
+
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds the -DDFU_TRACE diagnostic variant (in-kernel timeline records, scripts/trace_step.py);
+    the product library never contains that code."""
+    LIB = TRACE_LIB if trace else globals()["LIB"]
+    STAMP = globals()["STAMP"] + (".trace" if trace else "")
+    FLAGS = globals()["FLAGS"] + (["-DDFU_TRACE"] if trace else [])
+    bdir = os.path.join(HERE, "build", "trace") if trace else os.path.join(HERE, "build")
+    dig = _digest() + ("+trace" if trace else "")
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
     if not os.path.exists(NVCC):
         if os.path.exists(LIB):
             return LIB  # GPU box without a changed tree: use the prebuilt library that travelled with the snapshot
-        raise RuntimeError("nvcc not found and no prebuilt libdiffute_b200.so")
+        raise RuntimeError(f"nvcc not found and no prebuilt {os.path.basename(LIB)}")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -66,4 +75,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, trace="--trace" in sys.argv))

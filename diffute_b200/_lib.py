@@ -22,7 +22,8 @@ class GemmOperand(C.Structure):
         ("a_h", C.c_int32), ("a_w", C.c_int32), ("a_c", C.c_int32), ("a_plane", C.c_int32),
         ("b", C.c_void_p), ("b_rows", C.c_int32), ("b_ld", C.c_int32), ("b_plane", C.c_int32),
         ("ntaps", C.c_int32), ("k_per_tap", C.c_int32),
-        ("tap_dn", C.c_int8 * 9), ("tap_dy", C.c_int8 * 9), ("tap_dx", C.c_int8 * 9), ("_pad", C.c_int8 * 5),
+        ("tap_dn", C.c_int8 * 9), ("tap_dy", C.c_int8 * 9), ("tap_dx", C.c_int8 * 9), ("b_static", C.c_int8),
+        ("_pad", C.c_int8 * 4),
     ]
 
 
@@ -52,7 +53,8 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     from . import _build
-    path = _build.build()
+    # DFU_TRACE=1 loads the diagnostic build with in-kernel timeline records (diffute_b200/trace.py); never the default
+    path = _build.build(trace=os.environ.get("DFU_TRACE") == "1")
     if not os.path.exists(path):
         raise DfuError(f"{path} missing: the CUDA extension is required (no fallback)")
     L = C.CDLL(path)
@@ -102,6 +104,10 @@ SIGNATURES = {
     "dfu_attention": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _i, _i64,
                            _i, _vp, _sz, _vp]),
     "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _i64, _vp]),
+    "dfu_trace_set_gemm": (_i, [_vp]),
+    "dfu_trace_set_attn": (_i, [_vp]),
+    "dfu_trace_set_norm": (_i, [_vp]),
+    "dfu_trace_set_misc": (_i, [_vp]),
 }
 
 

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_ATTN | (p.kv_splits << 8));
   // No static shared memory: the dynamic window then starts 1024-byte aligned at the CTA's base, and the FP16 mode
   // needs 7 x 16 KiB + 128 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -114,7 +115,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_S = tmem_base;        // 128 columns
   const uint32_t tmem_O = tmem_base + 128;  // 64 columns
   const uint32_t tmem_X = tmem_base + 192;  // 4 spare columns: per-row exchange between the two softmax warpgroups
+  DFU_TR_MARK(5);
   pdl_wait();
+  DFU_TR_MARK(6);
 
   if (warp == 8) {
     // ===== TMA producer ======================================================================
@@ -289,6 +292,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       alpha_prev = alpha;
     }
     accumulate_o(nblk - 1);
+    DFU_TR_MARK(8);
     // total row sum = partial(wg 0) + partial(wg 1), added in that order by both threads
     {
       const uint32_t xs = tmem_X + lane_off + (nblk & 1) * 2;
@@ -333,6 +337,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  DFU_TR_END();
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -340,30 +345,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // Combine the kv_splits partial results of one (sample, head, query tile): O = sum_s O_s 2^((m_s - M) c2) / sum_s l_s
-// 2^((m_s - M) c2), slices in order (deterministic).  One 4-column quad per thread.
+// 2^((m_s - M) c2), slices in order (deterministic).  One 4-column quad per thread; every load of a thread (<= 8
+// slices x (m, l) + O quad) is issued before the first use, so the kernel costs one L2 round trip, not 2 x kv_splits.
+constexpr int kMaxKvSplits = 8;
 __global__ void __launch_bounds__(256) attn_merge_kernel(AttnParams p, int q_tiles) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_ATTN_MERGE);
   pdl_wait();
-  const int tile = blockIdx.x;                 // (b*heads + head)*q_tiles + q_tile
+  DFU_TR_MARK(6);
+  const int gidx = blockIdx.x * 256 + threadIdx.x;  // (tile, row, quad)
+  const int tile = gidx >> 11;                      // (b*heads + head)*q_tiles + q_tile
+  const int r = (gidx >> 4) & 127, cq = gidx & 15;
   const int q_tile = tile % q_tiles;
   const int bh = tile / q_tiles;
   const int head = bh % p.heads, b = bh / p.heads;
-  const size_t item0 = static_cast<size_t>(tile) * p.kv_splits;
-  for (int idx = threadIdx.x; idx < 128 * 16; idx += blockDim.x) {
-    const int r = idx >> 4, cq = idx & 15;
-    const int q = q_tile * kBQ + r;
-    if (q >= p.Nq) continue;
+  const int q = q_tile * kBQ + r;
+  if (q < p.Nq) {
+    const size_t item0 = static_cast<size_t>(tile) * p.kv_splits;
+    float2 ml[kMaxKvSplits];
+    float4 t[kMaxKvSplits];
+#pragma unroll
+    for (int s = 0; s < kMaxKvSplits; ++s)
+      if (s < p.kv_splits) {
+        ml[s] = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + ((item0 + s) * 128 + r) * 2));
+        t[s] = __ldcg(reinterpret_cast<const float4*>(p.ws_o + ((item0 + s) * 128 + r) * 64 + cq * 4));
+      }
     float M = -INFINITY;
-    for (int s = 0; s < p.kv_splits; ++s) M = fmaxf(M, __ldcg(p.ws_ml + ((item0 + s) * 128 + r) * 2));
+#pragma unroll
+    for (int s = 0; s < kMaxKvSplits; ++s)
+      if (s < p.kv_splits) M = fmaxf(M, ml[s].x);
     float L = 0.f;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < p.kv_splits; ++s) {
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + ((item0 + s) * 128 + r) * 2));
-      const float w = fast_exp2((ml.x - M) * p.scale_log2);
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(p.ws_o + ((item0 + s) * 128 + r) * 64 + cq * 4));
-      L += ml.y * w;
-      o.x += t.x * w; o.y += t.y * w; o.z += t.z * w; o.w += t.w * w;
-    }
+#pragma unroll
+    for (int s = 0; s < kMaxKvSplits; ++s)
+      if (s < p.kv_splits) {
+        const float w = fast_exp2((ml[s].x - M) * p.scale_log2);
+        L += ml[s].y * w;
+        o.x += t[s].x * w; o.y += t[s].y * w; o.z += t[s].z * w; o.w += t[s].w * w;
+      }
     const float inv = 1.0f / L;
     o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
     __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + cq * 4;
@@ -379,6 +398,7 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(AttnParams p, int q_til
       *reinterpret_cast<uint2*>(dst + p.out_plane_stride) = *reinterpret_cast<const uint2*>(lo);
     }
   }
+  DFU_TR_END();
 }
 
 static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, int planes, long long plane_stride) {
@@ -392,6 +412,8 @@ static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, 
 
 }  // namespace dfu
 
+DFU_TRACE_SETTER(dfu_trace_set_attn)
+
 using namespace dfu;
 
 static int attn_auto_splits(int B, int heads, int Nq, int Nk) {
@@ -404,7 +426,7 @@ static int attn_auto_splits(int B, int heads, int Nq, int Nk) {
   if (nblk < 4 || ctas >= 4 * sms) return 1;
   int s = (4 * sms + ctas - 1) / ctas;
   if (s > nblk / 2) s = nblk / 2;
-  if (s > 8) s = 8;
+  if (s > kMaxKvSplits) s = kMaxKvSplits;
   return s < 1 ? 1 : s;
 }
 
@@ -438,6 +460,7 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   const int nblk_all = (Nk + kBKV - 1) / kBKV;
   if (kv_splits <= 0) kv_splits = attn_auto_splits(B, heads, Nq, Nk);
   if (kv_splits > nblk_all) kv_splits = nblk_all;
+  DFU_REQUIRE(kv_splits <= kMaxKvSplits, "attention: kv_splits=%d > %d", kv_splits, kMaxKvSplits);
   int bps = (nblk_all + kv_splits - 1) / kv_splits;
   kv_splits = (nblk_all + bps - 1) / bps;  // no empty slices
   p.kv_splits = kv_splits;
@@ -464,6 +487,6 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   dim3 grid(q_tiles, heads, B * kv_splits);
   DFU_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream_), mQ, mK, mV, p));
   if (kv_splits > 1)
-    DFU_CHECK_CUDA(launch_k(attn_merge_kernel, dim3(B * heads * q_tiles), dim3(256), 0, static_cast<cudaStream_t>(stream_), p, q_tiles));
+    DFU_CHECK_CUDA(launch_k(attn_merge_kernel, dim3(B * heads * q_tiles * 8), dim3(256), 0, static_cast<cudaStream_t>(stream_), p, q_tiles));
   return DFU_OK;
 }

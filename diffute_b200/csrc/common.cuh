@@ -68,6 +68,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires,
+// instead of returning after ~50 cycles.  ncu showed 16 epilogue warps per SM spinning ~95 times each on the
+// accumulator barrier during the main loop (391k try_wait + clock reads per launch), taking issue slots from the
+// single-thread TMA producer and MMA issuer.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Long waits (epilogue warps waiting for the whole main loop): hardware sleep, bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dfu: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a protocol bug traps (process dies with an error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -87,6 +113,75 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// In-kernel timeline tracing (only in the -DDFU_TRACE build, libdiffute_b200_trace.so; the product library compiles
+// these macros to nothing).  One 12 x u64 record per CTA: [0] %gridid, [1] tag | bid << 32, [2] smid | nctas << 32,
+// [3] globaltimer at entry, [4] clock64 at entry, [5..9] clock64 phase marks, [10] clock64 at exit, [11] globaltimer
+// at exit.  g_tr[0] = next record index (atomic), g_tr[1] = capacity, records start at g_tr + 8.
+// ----------------------------------------------------------------------------------------------
+#ifdef DFU_TRACE
+static __device__ unsigned long long* g_tr = nullptr;
+__device__ __forceinline__ unsigned long long trace_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long* trace_begin(unsigned int tag) {
+  unsigned long long* base = g_tr;
+  if (!base) return nullptr;
+  const unsigned long long idx = atomicAdd(base, 1ull);
+  if (idx >= base[1]) return nullptr;
+  unsigned long long* r = base + 8 + idx * 12;
+  unsigned long long gid;
+  unsigned int smid;
+  asm volatile("mov.u64 %0, %%gridid;" : "=l"(gid));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  r[0] = gid;
+  r[1] = tag | (static_cast<unsigned long long>(bid) << 32);
+  r[2] = smid | (static_cast<unsigned long long>(gridDim.x * gridDim.y * gridDim.z) << 32);
+  r[3] = trace_gtime();
+  r[4] = clock64();
+#pragma unroll
+  for (int i = 5; i < 12; ++i) r[i] = 0;
+  return r;
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* r, int slot) {
+  if (r) r[slot] = clock64();
+}
+__device__ __forceinline__ void trace_end(unsigned long long* r) {
+  if (r) {
+    r[10] = clock64();
+    r[11] = trace_gtime();
+  }
+}
+// per-thread flavour (simple kernels: thread 0 owns the record in a register)
+#define DFU_TR_BEGIN(tag) unsigned long long* _tr = (threadIdx.x == 0 && threadIdx.y == 0) ? dfu::trace_begin(tag) : nullptr
+#define DFU_TR_MARK(slot) dfu::trace_mark(_tr, slot)
+#define DFU_TR_END() dfu::trace_end(_tr)
+// CTA-shared flavour (warp-specialised kernels: the record pointer lives in shared memory, any thread may mark)
+#define DFU_TR_SHARED_DECL() __shared__ unsigned long long* _trs
+#define DFU_TR_SHARED_BEGIN(tag) do { if (threadIdx.x == 0) _trs = dfu::trace_begin(tag); } while (0)
+#define DFU_TR_SHARED_MARK(slot) dfu::trace_mark(_trs, slot)
+#define DFU_TR_SHARED_END() dfu::trace_end(_trs)
+#define DFU_TRACE_SETTER(name) \
+  extern "C" int name(void* p) { return cudaMemcpyToSymbol(dfu::g_tr, &p, sizeof(p)) == cudaSuccess ? 0 : -2; }
+#else
+#define DFU_TR_BEGIN(tag) do {} while (0)
+#define DFU_TR_MARK(slot) do {} while (0)
+#define DFU_TR_END() do {} while (0)
+#define DFU_TR_SHARED_DECL() do {} while (0)
+#define DFU_TR_SHARED_BEGIN(tag) do {} while (0)
+#define DFU_TR_SHARED_MARK(slot) do {} while (0)
+#define DFU_TR_SHARED_END() do {} while (0)
+#define DFU_TRACE_SETTER(name) extern "C" int name(void*) { return -1; }
+#endif
+// kernel tags of the trace records
+enum : unsigned int {
+  TR_GEMM = 1, TR_SPLITK_REDUCE, TR_ATTN, TR_ATTN_MERGE, TR_GN_STATS, TR_GN_FINALIZE, TR_GN_APPLY, TR_GN_FUSED,
+  TR_LAYERNORM, TR_CAST, TR_TEMB, TR_GEMV, TR_CONV_IN, TR_CONV_OUT, TR_MISC
+};
 
 // ----------------------------------------------------------------------------------------------
 // Grid-wide barrier for grids whose CTAs are all co-resident (the host checks occupancy before choosing a kernel
@@ -131,10 +226,11 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_
 }
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   float4 v;
+  // volatile (ordered against the volatile cluster barriers) but no memory clobber: independent global loads and
+  // stores around it may be scheduled freely, and consecutive remote loads pipeline
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr)
-               : "memory");
+               : "r"(addr));
   return v;
 }
 
@@ -263,7 +359,22 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // small math helpers
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (diffusers GEGLU uses F.gelu default = erf form).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7
+// absolute, below the fp16 rounding of the result by three orders of magnitude) in ~12 instructions instead of libm
+// erff's ~45: the GEGLU epilogue is instruction-issue bound.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));  // argument in [1, inf): no special cases
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float r = fmaf(-p * t, e, 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
 // RN split of an fp32 value into fp16 hi + fp16 lo (x ~= hi + lo to ~22 bits)
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {

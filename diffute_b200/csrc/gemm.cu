@@ -22,11 +22,12 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int kEpiThreads = 256;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KiB smem slot for A (box may fill fewer rows)
 
 struct GroupDev {
   int a_mode, ntaps, nchunks, a_plane, b_plane, kb_per_pass;
+  int b_static;  // B of this group is a constant (weights): may be fetched before the producer kernel completes
   int8_t dn[9], dy[9], dx[9];
 };
 
@@ -81,15 +82,20 @@ __device__ __forceinline__ void store_f16x4(__half* dst, float4 v, bool lo_plane
   }
 }
 
+// (the epilogue is instruction-issue bound — ~2000 cycles per 32-column chunk round at 16 epilogue warps per SM, measured
+// with scripts/trace_step.py — so everything per-row is hoisted by the callers and alpha == 1 costs nothing)
 __device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, float4 v) {
-  v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
+  if (e.alpha != 1.0f) {
+    v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
+  }
   if (e.bias) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n));
     v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
   if (e.rowvec) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(
-        e.rowvec + static_cast<size_t>(m / e.rows_per_sample) * e.rowvec_ld + n));
+    // one sample per 128-row tile is the common case (rows_per_sample >= 128): the division is then a compare
+    const int smp = (m < e.rows_per_sample) ? 0 : m / e.rows_per_sample;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(e.rowvec + static_cast<size_t>(smp) * e.rowvec_ld + n));
     v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
   return v;
@@ -172,13 +178,79 @@ __device__ __forceinline__ void reduce_quad(const float* __restrict__ ws, int sp
 }
 
 // ---------------------------------------------------------------------------------------------
+// cluster split-K second stage (epilogue threads of one CTA): rows [split*128/S, (split+1)*128/S) of the tile, summed
+// over the S partial tiles parked in the cluster's shared memories.  All S remote loads of a quad (and its residual)
+// are in flight before the first add: the loop costs DSMEM bandwidth, not S serial ~200-cycle round trips.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void cluster_reduce(const GemmKernelParams& p, const uint8_t* smem, int split, int n_tile0,
+                                               int m0, int x0, int y0, int img0) {
+  constexpr int rows_per = kBlockM / S;
+  const bool geglu = p.e.epi == DFU_EPI_GEGLU;
+  const int qpr = geglu ? p.block_n / 8 : p.block_n / 4;
+  const int ldp = p.block_n + 4;
+  const uint32_t part0 = smem_u32(smem);
+  uint32_t peer[S];
+#pragma unroll
+  for (int q = 0; q < S; ++q) peer[q] = dsmem_addr(part0, static_cast<uint32_t>(q));
+  const int te = threadIdx.x - 64;
+  for (int idx = te; idx < rows_per * qpr; idx += kEpiThreads) {
+    const int rr = split * rows_per + idx / qpr;
+    const int qi = idx % qpr;
+    const int col = geglu ? (qi >> 2) * 32 + (qi & 3) * 4 : qi * 4;
+    int m;
+    bool valid;
+    if (p.conv) {
+      const int ix = rr % p.bw;
+      const int t = rr / p.bw;
+      const int iy = t % p.bh;
+      const int in = t / p.bh;
+      const int x = x0 + ix, y = y0 + iy, img = img0 + in;
+      valid = (in < p.bn) && (x < p.W) && (y < p.H) && (img < p.B);
+      m = (img * p.H + y) * p.W + x;
+    } else {
+      m = m0 + rr;
+      valid = m < p.e.M;
+    }
+    if (!valid) continue;
+    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!geglu && p.e.residual)
+      rs = *reinterpret_cast<const float4*>(p.e.residual + static_cast<size_t>(m) * p.e.ldr + n_tile0 + col);
+    const uint32_t off = static_cast<uint32_t>(rr * ldp + col) * 4u;
+    float4 t[S], u[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) t[q] = ld_dsmem_f4(peer[q] + off);
+    if (geglu) {
+#pragma unroll
+      for (int q = 0; q < S; ++q) u[q] = ld_dsmem_f4(peer[q] + off + 64);
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      a.x += t[q].x; a.y += t[q].y; a.z += t[q].z; a.w += t[q].w;
+    }
+    if (geglu) {
+#pragma unroll
+      for (int q = 0; q < S; ++q) {
+        g.x += u[q].x; g.y += u[q].y; g.z += u[q].z; g.w += u[q].w;
+      }
+      epi_geglu_quad(p.e, m, n_tile0 + col, a, g);
+    } else {
+      epi_quad_res(p.e, m, n_tile0 + col, a, rs);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ GemmKernelParams p) {
   pdl_trigger();
+  DFU_TR_SHARED_DECL();
+  DFU_TR_SHARED_BEGIN(TR_GEMM | (p.splits << 8) | (p.cluster << 16) | (p.block_n << 20));
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -240,15 +312,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
+  if (threadIdx.x == 0) DFU_TR_SHARED_MARK(5);
+  // the prologue above overlapped the previous kernel; every role waits for it (griddepcontrol.wait) right before its
+  // first access to data that kernel produced — the TMA producer only after it has requested the weight tiles
 
   if (warp == 0) {
     // ===== TMA producer =====================================================================
     if (lane == 0) {
       const int kbg0 = p.g[0].kb_per_pass * p.npass;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      // k-block -> (group, pass, tap, channel chunk) and the two loads of that k-block
+      auto issue = [&](int kb, int stage, bool load_a, bool load_b) {
         int r = kb, gi = 0;
         if (r >= kbg0) {
           r -= kbg0;
@@ -263,17 +336,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int b_sel = (pass == 2) ? G.b_plane : 0;
         const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
         const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * stage_bytes;
         uint8_t* sB = sA + kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes[gi] + p.b_tx_bytes);
-        if (G.a_mode == 0) {
-          tma_load_2d(sA, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
-        } else {
-          tma_load_4d(sA, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
-                      img0 + G.dn[tap] + a_sel);
+        if (load_b) {  // the k-block's first load also arms the barrier with the bytes of BOTH operands
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes[gi] + p.b_tx_bytes);
+          tma_load_2d(sB, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, n_tile0 + b_sel);
         }
-        tma_load_2d(sB, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, n_tile0 + b_sel);
+        if (load_a) {
+          if (G.a_mode == 0) {
+            tma_load_2d(sA, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
+          } else {
+            tma_load_4d(sA, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
+                        img0 + G.dn[tap] + a_sel);
+          }
+        }
+      };
+      // Weights do not depend on the previous kernel: the B tiles of the first ring-full of k-blocks are requested
+      // BEFORE griddepcontrol.wait, so their HBM latency (and, for the weight-streaming deep levels, a good part of
+      // the streaming itself) overlaps the producer kernel's tail.
+      const bool pre = p.g[0].b_static && (p.ngroups == 1 || p.g[1].b_static);
+      const int npre = pre ? min(p.stages, kb1 - kb0) : 0;
+      for (int i = 0; i < npre; ++i) issue(kb0 + i, i, false, true);
+      pdl_wait();  // activations (A) are valid from here on
+      DFU_TR_SHARED_MARK(6);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (kb - kb0 < npre) {
+          issue(kb, stage, true, false);
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          issue(kb, stage, true, true);
+        }
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -289,6 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (kb == kb0) DFU_TR_SHARED_MARK(7);
         const uint32_t sA = smem_u32(smem + stage * stage_bytes);
         const uint32_t sB = sA + kABytes;
         const uint64_t adesc = umma_desc_sw128(sA);
@@ -326,26 +421,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       m = m0 + r;
       valid = m < p.e.M;
     }
-    mbar_wait(&tmem_full_bar, 0);
+    // ---- everything that does not need the accumulator happens while the main loop runs ----
+    const bool direct = p.splits == 1;
+    const bool geglu = direct && p.e.epi == DFU_EPI_GEGLU;
+    const bool has_res = direct && !geglu && p.e.residual != nullptr;
+    if (warp == 2 && p.e.bias != nullptr && lane * 8 < p.block_n)  // weights: before the wait (1 KiB = 32 sectors)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.e.bias + n_tile0 + lane * 8));
+    // the 32 rows of this warp are the same for every column chunk: (m, valid) of the rows this lane stores, once
+    const int vmask = valid ? 1 : 0;
+    int mrs[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = geglu ? (it & 3) * 8 + (lane >> 2) : it * 4 + (lane >> 3);
+      const int mr = __shfl_sync(0xffffffffu, m, row);
+      const int vr = __shfl_sync(0xffffffffu, vmask, row);
+      mrs[it] = vr ? mr : -1;
+    }
+    const int cq = lane & 7;
+    pdl_wait();  // residual / rowvec are activations, and the outputs may alias buffers earlier kernels still read
+    if (warp == 2 && p.e.rowvec != nullptr && lane * 8 < p.block_n)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.e.rowvec + static_cast<size_t>((valid ? m : 0) / p.e.rows_per_sample) * p.e.rowvec_ld + n_tile0 + lane * 8));
+    // residual quads are requested one chunk ahead (the first chunk's during the main loop): their L2 latency never
+    // sits between the accumulator read and the stores
+    // (one register buffer: each quad is re-requested for the next chunk right after it has been consumed)
+    float4 res[8];
+    auto fetch_res1 = [&](int c, int it) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_res && (c + cq * 4 < p.block_n) && mrs[it] >= 0)
+        t = *reinterpret_cast<const float4*>(p.e.residual + static_cast<size_t>(mrs[it]) * p.e.ldr + n_tile0 + c + cq * 4);
+      return t;
+    };
+#pragma unroll
+    for (int it = 0; it < 8; ++it) res[it] = fetch_res1(cg * 32, it);
+    mbar_wait_sleep(&tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) DFU_TR_SHARED_MARK(8);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // TMEM gives each thread one output row; a per-warp smem transpose turns that into row-contiguous 16-byte
     // quads per lane so global traffic is coalesced (4 full 128-byte lines per warp instruction).
-    // (the operand ring is idle once tmem_full has fired, so its first 18 KiB double as the staging area)
+    // (the operand ring is idle once tmem_full has fired, so its first 36 KiB double as the staging area)
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * kStageFloats;
-    const int vmask = valid ? 1 : 0;
+#pragma unroll 1  // (one copy of the epilogue body: unrolled x4 the kernel outgrew the instruction cache)
     for (int c = cg * 32; c < p.block_n; c += 64) {
       uint32_t raw[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
       tmem_ld_wait();
+      const int ncol = p.block_n - c;  // columns of this chunk inside the tile (block_n may end mid-chunk)
       if (p.cluster > 1) {
         // cluster split-K: park this slice's fp32 partial tile in OWN shared memory (row r at r * (block_n + 4))
         float* prow = reinterpret_cast<float*>(smem) + static_cast<size_t>(r) * (p.block_n + 4) + c;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(prow + 4 * i) =
-              make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
-                          __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+          if (4 * i < ncol)
+            *reinterpret_cast<float4*>(prow + 4 * i) =
+                make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                            __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
         continue;
       }
       __syncwarp();
@@ -356,44 +486,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         __uint_as_float(raw[4 * i + 3]));
       __syncwarp();
       const int n = n_tile0 + c;
-      if (p.splits == 1 && p.e.epi == DFU_EPI_GEGLU) {
+      if (geglu) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + (lane >> 2), cq = lane & 3;
-          const int mr = __shfl_sync(0xffffffffu, m, row);
-          const int vr = __shfl_sync(0xffffffffu, vmask, row);
-          const float4 a = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
-          const float4 g = *reinterpret_cast<const float4*>(stage + row * kStageLd + 16 + cq * 4);
-          if (vr) epi_geglu_quad(p.e, mr, n + cq * 4, a, g);
+          const int row = it * 8 + (lane >> 2), cq4 = lane & 3;
+          const float4 a = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq4 * 4);
+          const float4 g = *reinterpret_cast<const float4*>(stage + row * kStageLd + 16 + cq4 * 4);
+          if (mrs[it] >= 0) epi_geglu_quad(p.e, mrs[it], n + cq4 * 4, a, g);
         }
       } else {
-        // all 8 rows' residual quads are requested before any is consumed: one memory latency per chunk, not eight
-        int mrs[8];
-        float4 res[8];
-        const bool has_res = (p.splits == 1) && (p.e.residual != nullptr);
+        const bool qok = cq * 4 < ncol;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
-          const int mr = __shfl_sync(0xffffffffu, m, row);
-          const int vr = __shfl_sync(0xffffffffu, vmask, row);
-          mrs[it] = vr ? mr : -1;
-          res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res && vr)
-            res[it] = *reinterpret_cast<const float4*>(p.e.residual + static_cast<size_t>(mr) * p.e.ldr + n + (lane & 7) * 4);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + (lane >> 3), cq = lane & 7;
           const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
-          if (mrs[it] >= 0) {
-            if (p.splits > 1)
+          if (qok && mrs[it] >= 0) {
+            if (!direct)
               __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mrs[it]) * p.e.N + n + cq * 4), v);
             else
               epi_quad_res(p.e, mrs[it], n + cq * 4, v, res[it]);
           }
+          if (c + 64 < p.block_n) res[it] = fetch_res1(c + 64, it);
         }
       }
     }
+    if (threadIdx.x == 64) DFU_TR_SHARED_MARK(9);
     if (p.splits > 1 && p.sync != nullptr) {
       // Fused second stage (all CTAs of this launch are co-resident): once every slice has parked its partial tile
       // in the L2-resident workspace, the epilogue threads of ALL CTAs share the reduction + fused epilogue, one
@@ -414,47 +531,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // tiles (read through distributed shared memory, slice order => deterministic) and runs the fused epilogue ----
     cluster_sync_all();
     if (warp >= 2) {
-      const int S = p.cluster;
-      const int rows_per = kBlockM / S;
-      const bool geglu = p.e.epi == DFU_EPI_GEGLU;
-      const int qpr = geglu ? p.block_n / 8 : p.block_n / 4;
-      const int ldp = p.block_n + 4;
-      const uint32_t part0 = smem_u32(smem);
-      const int te = threadIdx.x - 64;
-      for (int idx = te; idx < rows_per * qpr; idx += kEpiThreads) {
-        const int rr = split * rows_per + idx / qpr;
-        const int qi = idx % qpr;
-        const int col = geglu ? (qi >> 2) * 32 + (qi & 3) * 4 : qi * 4;
-        int m;
-        bool valid;
-        if (p.conv) {
-          const int ix = rr % p.bw;
-          const int t = rr / p.bw;
-          const int iy = t % p.bh;
-          const int in = t / p.bh;
-          const int x = x0 + ix, y = y0 + iy, img = img0 + in;
-          valid = (in < p.bn) && (x < p.W) && (y < p.H) && (img < p.B);
-          m = (img * p.H + y) * p.W + x;
-        } else {
-          m = m0 + rr;
-          valid = m < p.e.M;
-        }
-        if (!valid) continue;
-        const uint32_t loc = part0 + static_cast<uint32_t>(rr * ldp + col) * 4u;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-        for (int q = 0; q < S; ++q) {
-          const uint32_t ra = dsmem_addr(loc, static_cast<uint32_t>(q));
-          const float4 t = ld_dsmem_f4(ra);
-          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-          if (geglu) {
-            const float4 u = ld_dsmem_f4(ra + 64);
-            g.x += u.x; g.y += u.y; g.z += u.z; g.w += u.w;
-          }
-        }
-        if (geglu)
-          epi_geglu_quad(p.e, m, n_tile0 + col, a, g);
-        else
-          epi_quad(p.e, m, n_tile0 + col, a);
+      switch (p.cluster) {
+        case 2: cluster_reduce<2>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
+        case 4: cluster_reduce<4>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
+        default: cluster_reduce<8>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
       }
     }
     cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
@@ -462,6 +542,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DFU_TR_SHARED_END();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -470,11 +551,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_SPLITK_REDUCE);
   pdl_wait();
+  DFU_TR_MARK(6);
   const long long total = static_cast<long long>(e.M) * (e.epi == DFU_EPI_GEGLU ? e.N / 8 : e.N / 4);
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x)
     reduce_quad(ws, splits, e, idx);
+  DFU_TR_END();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -535,13 +619,14 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
     // cycles, the SS-mode operand fetch (4 KiB of A + 32*bn bytes of B at 128 B/clk) 32 + bn/4 — so tiles narrower
     // than 128 columns are operand-bandwidth bound and parallelism is bought with split-K instead.  CTAs beyond one
     // per SM serialise on the tensor pipe; a split adds a partial-tile round trip through L2 and a second launch.
-    const int cands[] = {256, 160, 128, 96, 64, 32};
+    const int cands[] = {256, 160, 128, 96, 80, 64, 32};
     const int scand[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
     double best = 1e30;
     int best_bn = 0, best_s = 1;
     for (int c : cands) {
       if (d->n % c != 0) continue;
       if (d->block_n > 0 && c != d->block_n) continue;
+      if (d->epi == DFU_EPI_GEGLU && c % 32 != 0) continue;
       const int tiles = pl->tiles_m * (d->n / c);
       const double per_k16 = (c / 2.0 > 32.0 + c / 4.0) ? c / 2.0 : 32.0 + c / 4.0;
       for (int sp : scand) {
@@ -567,7 +652,8 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
     bn_ = best_bn;
     splits = best_s;
   }
-  DFU_REQUIRE(bn_ % 32 == 0 && bn_ <= 256 && d->n % bn_ == 0, "gemm: bad block_n=%d for n=%d", bn_, d->n);
+  DFU_REQUIRE(bn_ % 16 == 0 && bn_ >= 16 && bn_ <= 256 && d->n % bn_ == 0, "gemm: bad block_n=%d for n=%d", bn_, d->n);
+  DFU_REQUIRE(d->epi != DFU_EPI_GEGLU || bn_ % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0, got %d", bn_);
   pl->block_n = bn_;
   pl->tiles_n = d->n / bn_;
   DFU_REQUIRE(splits >= 1 && splits <= total_kb, "gemm: bad splits=%d (k-blocks %d)", splits, total_kb);
@@ -576,9 +662,17 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
   int stages = d->stages;
   const size_t stage_bytes = kABytes + static_cast<size_t>(bn_) * 128;
   if (stages <= 0) {
-    stages = bn_ > 160 ? 4 : 3;  // <=160: ~108 KiB -> two CTAs per SM overlap epilogue and main loop
+    // ~1.4 us of TMA latency (measured, scripts/trace_step.py) at >= 64 B/clk per SM wants ~100 KiB in flight; stay
+    // under half the SM so that the NEXT kernel's CTA can be co-resident and prefetch its weights (PDL)
+    stages = static_cast<int>((110 * 1024) / stage_bytes);
+    if (stages < 3) stages = 3;
+  }
+  {
+    const int kb_cta = (total_kb + splits - 1) / splits;
+    if (stages > kb_cta) stages = kb_cta < 2 ? 2 : kb_cta;
   }
   if (stages > kMaxStages) stages = kMaxStages;
+  while (stages > 2 && stages * stage_bytes + 1024 > 226 * 1024) --stages;
   pl->stages = stages;
   pl->smem_bytes = stages * stage_bytes + 1024;  // >= kStageBytes: the epilogue staging reuses the ring
   DFU_REQUIRE(pl->smem_bytes <= 226 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
@@ -645,6 +739,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     G.a_plane = o.a_plane;
     G.b_plane = o.b_plane;
     G.kb_per_pass = o.ntaps * G.nchunks;
+    G.b_static = o.b_static;
     for (int t = 0; t < 9; ++t) {
       G.dn[t] = o.tap_dn[t];
       G.dy[t] = o.tap_dy[t];
@@ -740,6 +835,8 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
 }
 
 }  // namespace dfu
+
+DFU_TRACE_SETTER(dfu_trace_set_gemm)
 
 extern "C" {
 int dfu_gemm(const DfuGemm* desc, void* stream) {

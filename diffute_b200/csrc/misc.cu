@@ -14,7 +14,9 @@ namespace dfu {
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int B, int dim, int flip_sin_to_cos,
                                       float freq_shift, float* __restrict__ out) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_TEMB);
   pdl_wait();
+  DFU_TR_MARK(6);
   const int half = dim / 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
     const int b = i / half, k = i % half;
@@ -43,7 +45,9 @@ __global__ void __launch_bounds__(256)
 gemv_kernel(const float* __restrict__ x, int B, int K, int ldx, const float* __restrict__ W,
             const float* __restrict__ bias, int N, int silu_in, int silu_out, float* __restrict__ out, int ldo) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_GEMV);
   pdl_wait();
+  DFU_TR_MARK(6);
   extern __shared__ float xs[];  // [B][K] activated input
   for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
     const int b = i / K, k = i % K;
@@ -98,7 +102,9 @@ __global__ void __launch_bounds__(256)
 conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const float* __restrict__ wt,
                      const float* __restrict__ bias, int Cout, float pre_scale, float* __restrict__ out) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_CONV_IN);
   pdl_wait();
+  DFU_TR_MARK(6);
   // block: kSmallInPix consecutive output pixels x all Cout; input patches staged in smem; weights are stored
   // [Cin*k*k][Cout] so that consecutive lanes (consecutive output channels) read consecutive addresses.
   extern __shared__ float sm[];  // [kSmallInPix][K]
@@ -176,7 +182,9 @@ struct SmallOut {
 
 __global__ void __launch_bounds__(256) conv_small_out_kernel(SmallOut p) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_CONV_OUT);
   pdl_wait();
+  DFU_TR_MARK(6);
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long npix = static_cast<long long>(p.B) * p.H * p.W;
@@ -240,7 +248,9 @@ __global__ void __launch_bounds__(256)
 axpbypcz_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ n, float a, float b,
                 float c, float* __restrict__ y, long long total) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_MISC);
   pdl_wait();
+  DFU_TR_MARK(6);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v = a * x[i] + b * e[i];
@@ -256,7 +266,9 @@ sched_step_kernel(const float* __restrict__ x, const float* __restrict__ m, cons
                   float a1, float p0, float d0, float d1, float sn, int clip, float* __restrict__ y,
                   float* __restrict__ x0_out, long long total) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_MISC);
   pdl_wait();
+  DFU_TR_MARK(6);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float xv = x[i], mv = m[i];
@@ -274,7 +286,9 @@ __global__ void __launch_bounds__(256)
 axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ ca,
                   const float* __restrict__ cb, float* __restrict__ y, long long per_row, long long total) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_MISC);
   pdl_wait();
+  DFU_TR_MARK(6);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / per_row;
@@ -287,7 +301,9 @@ __global__ void __launch_bounds__(256)
 gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ eps, int B, int Cz, int HW,
                        float scale, float* __restrict__ z) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_MISC);
   pdl_wait();
+  DFU_TR_MARK(6);
   const long long total = static_cast<long long>(B) * Cz * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -312,7 +328,9 @@ __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ s, int rows, int n, int lds, float scale, __half* __restrict__ p16,
                     int ldp, int planes, long long plane_stride) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_MISC);
   pdl_wait();
+  DFU_TR_MARK(6);
   const int row = blockIdx.x;
   if (row >= rows) return;
   __shared__ float red[32];
@@ -347,7 +365,9 @@ softmax_rows_kernel(const float* __restrict__ s, int rows, int n, int lds, float
 __global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, int ld_in, long long in_plane,
                                      __half* __restrict__ out, long long out_plane) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_MISC);
   pdl_wait();
+  DFU_TR_MARK(6);
   __shared__ __half tile[32][33];
   const __half* src = in + blockIdx.z * in_plane;
   __half* dst = out + blockIdx.z * out_plane;
@@ -372,6 +392,8 @@ static int ew_grid2(long long total, int threads) {
 }
 
 }  // namespace dfu
+
+DFU_TRACE_SETTER(dfu_trace_set_misc)
 
 using namespace dfu;
 

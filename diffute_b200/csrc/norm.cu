@@ -34,7 +34,9 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
                                 unsigned int* __restrict__ counters, float2* __restrict__ stats, double count,
                                 float eps) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_GN_STATS);
   pdl_wait();
+  DFU_TR_MARK(6);
   extern __shared__ float sm[];  // [TY][2][C] per-row-of-threads channel sums, reduced in a fixed order (deterministic)
   const int C = s.C0 + s.C1;
   const int cpg = C / groups;
@@ -77,6 +79,7 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
     __stcg(&partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * groups + tid], make_float2(a, q));
     __threadfence();
   }
+  DFU_TR_END();
   if (counters == nullptr) return;
   // The LAST chunk of this sample to finish turns the partials into (mean, rstd): no waiting (an arrival counter, not
   // a barrier), a fixed summation order (deterministic), and the apply kernel starts from 32 ready numbers.
@@ -128,7 +131,9 @@ __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float2* __restrict__ partial, int nchunks, int groups, double count, float eps,
                    float2* __restrict__ stats) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_GN_FINALIZE);
   pdl_wait();
+  DFU_TR_MARK(6);
   __shared__ double s_sum[256], s_sq[256];
   const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float2* pp = partial + static_cast<size_t>(b) * nchunks * groups + g;
@@ -201,14 +206,29 @@ __device__ __forceinline__ void store_split4(__half* dst, long long plane_stride
   }
 }
 
-__global__ void gn_apply_kernel(GnApply a) {
+__global__ void __launch_bounds__(1024, 1) gn_apply_kernel(GnApply a) {
   pdl_trigger();
-  pdl_wait();
+  DFU_TR_BEGIN(TR_GN_APPLY);
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.s.C0 + a.s.C1;
   const int cpg = C / a.groups;
   const int b = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int c = threadIdx.x * 4;
+  // affine parameters are weights (HBM every step): fetched before waiting for the producer kernel
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  pdl_wait();
+  DFU_TR_MARK(6);
+  // the activations do not depend on the statistics: request them first so both latencies overlap
+  const int p0 = blockIdx.x * a.pix_per_cta;
+  const int p1 = min(p0 + a.pix_per_cta, a.s.HW);
+  float4 vin[kGnPixPerThread];
+#pragma unroll
+  for (int j = 0; j < kGnPixPerThread; ++j) {
+    const int p = p0 + threadIdx.y + j * blockDim.y;
+    vin[j] = (p < p1) ? gn_load(a.s, b, p, threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (a.stats) {
     if (tid < a.groups) {
       const float2 t = a.stats[b * a.groups + tid];
@@ -250,23 +270,15 @@ __global__ void gn_apply_kernel(GnApply a) {
     }
   }
   __syncthreads();
-  const int c = threadIdx.x * 4;
-  float mu[4], rs[4], ga[4], be[4];
+  DFU_TR_MARK(7);
+  float mu[4], rs[4];
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float be[4] = {be4.x, be4.y, be4.z, be4.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int g = (c + i) / cpg;
     mu[i] = s_mean[g];
     rs[i] = s_rstd[g];
-    ga[i] = a.gamma[c + i];
-    be[i] = a.beta[c + i];
-  }
-  const int p0 = blockIdx.x * a.pix_per_cta;
-  const int p1 = min(p0 + a.pix_per_cta, a.s.HW);
-  float4 vin[kGnPixPerThread];
-#pragma unroll
-  for (int j = 0; j < kGnPixPerThread; ++j) {
-    const int p = p0 + threadIdx.y + j * blockDim.y;
-    vin[j] = (p < p1) ? gn_load(a.s, b, p, threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
   for (int j = 0; j < kGnPixPerThread; ++j) {
@@ -286,6 +298,7 @@ __global__ void gn_apply_kernel(GnApply a) {
     if (a.out32) *reinterpret_cast<float4*>(a.out32 + off) = y;
     if (a.raw16) store_split4(a.raw16 + off, a.plane_stride, a.planes, v);
   }
+  DFU_TR_END();
 }
 
 // =============================================================================================
@@ -413,47 +426,62 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
                  const float* __restrict__ beta, float eps, __half* __restrict__ out16, int planes,
                  long long plane_stride) {
   pdl_trigger();
-  pdl_wait();
+  DFU_TR_BEGIN(TR_LAYERNORM);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
   const int C4 = C >> 2;
-  const float4* row = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
-  float4 v[kLnMaxQuads];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxQuads; ++i) {
-    const int q = lane + 32 * i;
-    if (q < C4) {
-      v[i] = row[q];
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
+  // gamma / beta are weights (they stream from HBM every step): pull them into L1 BEFORE waiting for the producer
+  // kernel, so that their latency overlaps its tail instead of sitting on the critical path after the reductions
+  // (a prefetch, not a register load: 80 more live registers would halve the occupancy)
+  if ((threadIdx.x >> 5) == 0) {
+    for (int o = lane * 32; o < C; o += 32 * 32) {  // one 128-byte line per lane and round
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gamma + o));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(beta + o));
     }
   }
-  const float mean = warp_sum(s) / C;
-  float ss = 0.f;
+  pdl_wait();
+  DFU_TR_MARK(6);
+  if (warp < M) {
+    const float4* row = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
+    float4 v[kLnMaxQuads];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxQuads; ++i) {
-    const int q = lane + 32 * i;
-    if (q < C4) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      ss += a * a + b * b + c * c + d * d;
+    for (int i = 0; i < kLnMaxQuads; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) v[i] = row[q];
+    }
+#pragma unroll
+    for (int i = 0; i < kLnMaxQuads; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxQuads; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        ss += a * a + b * b + c * c + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxQuads; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[i].w - mean) * rstd * g.w + b.w;
+        store_split4(out16 + static_cast<size_t>(warp) * C + q * 4, plane_stride, planes, y);
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
-#pragma unroll
-  for (int i = 0; i < kLnMaxQuads; ++i) {
-    const int q = lane + 32 * i;
-    if (q < C4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
-      float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      store_split4(out16 + static_cast<size_t>(warp) * C + q * 4, plane_stride, planes, y);
-    }
-  }
+  DFU_TR_END();
 }
 
 // =============================================================================================
@@ -463,7 +491,9 @@ __global__ void __launch_bounds__(256)
 cast_kernel(const float* __restrict__ x, int B, int H, int W, int C, int mode, __half* __restrict__ out, int planes,
             long long plane_stride) {
   pdl_trigger();
+  DFU_TR_BEGIN(TR_CAST);
   pdl_wait();
+  DFU_TR_MARK(6);
   const int C4 = C >> 2;
   const long long total = static_cast<long long>(B) * H * W * C4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -493,6 +523,7 @@ cast_kernel(const float* __restrict__ x, int B, int H, int W, int C, int mode, _
       store_split4(out + o, plane_stride, planes, v);
     }
   }
+  DFU_TR_END();
 }
 
 static int ew_grid(long long total, int threads) {
@@ -505,25 +536,34 @@ static int ew_grid(long long total, int threads) {
 
 }  // namespace dfu
 
+DFU_TRACE_SETTER(dfu_trace_set_norm)
+
 using namespace dfu;
 
 // block (C/4, ty), ty rows of threads each walking kGnPixPerThread pixels -> ppc pixels per CTA
-static void gn_geometry(int HW, int C, int* ty, int* ppc, int* chunks) {
+static void gn_geometry(int B, int HW, int C, int* ty, int* ppc, int* chunks) {
   const int C4 = C / 4;
   int t = 512 / C4;
   if (t < 1) t = 1;
   if (t > 16) t = 16;
   if (t > HW) t = HW;
+  auto nchunks = [&](int tt) { return (HW + tt * kGnPixPerThread - 1) / (tt * kGnPixPerThread); };
+  // a grid a little over one CTA per SM runs as two waves (measured: 171 CTAs at 64x64x320): grow the CTA, up to
+  // 1024 threads, until the grid fits one wave
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  while (static_cast<long long>(nchunks(t)) * B > sms && static_cast<long long>(nchunks(t)) * B <= sms + sms / 2 &&
+         (t + 1) * C4 <= 1024 && t < 16 && t < HW)
+    ++t;
   *ty = t;
   *ppc = t * kGnPixPerThread;
-  *chunks = (HW + *ppc - 1) / *ppc;
+  *chunks = nchunks(t);
 }
 
 extern "C" {
 
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups) {
   int ty, ppc, chunks;
-  gn_geometry(HW, C, &ty, &ppc, &chunks);
+  gn_geometry(B, HW, C, &ty, &ppc, &chunks);
   return static_cast<size_t>(B) * (chunks + 1) * groups * sizeof(float2);
 }
 
@@ -542,7 +582,7 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
     return DFU_ERR_WORKSPACE;
   }
   int ty, ppc, chunks;
-  gn_geometry(HW, C, &ty, &ppc, &chunks);
+  gn_geometry(B, HW, C, &ty, &ppc, &chunks);
   const int C4 = C / 4;
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};

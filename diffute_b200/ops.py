@@ -186,6 +186,7 @@ def matrix_operand(op, a16: torch.Tensor, w16: torch.Tensor, K: int, planes: int
     op.a_plane = a16.stride(0) // a16.stride(1) if planes > 1 else a16.shape[1]
     op.a_rows = op.a_plane * (planes - 1) + a16.shape[1]
     op.b = w16.data_ptr()
+    op.b_static = 0 if w16.dim() == 3 else 1  # packed weights never change inside a step; an activation used as B does
     if w16.dim() == 3:
         op.b_ld = w16.stride(1)
         op.b_plane = w16.stride(0) // w16.stride(1) if planes > 1 else w16.shape[1]
@@ -208,6 +209,7 @@ def image_operand(op, a16: torch.Tensor, w16: torch.Tensor, planes: int, taps, i
     op.a_h, op.a_w, op.a_c = h, w, c
     op.a_plane = imgs_per_plane
     op.b = w16.data_ptr()
+    op.b_static = 1
     op.b_rows = w16.shape[0]
     op.b_ld = w16.shape[1]
     op.b_plane = w16.shape[0] // planes

@@ -63,7 +63,8 @@ typedef struct DfuGemmOperand {
   int8_t tap_dn[9];     /* per tap: image offset (parity plane for stride-2), row offset, column offset */
   int8_t tap_dy[9];
   int8_t tap_dx[9];
-  int8_t _pad[5];
+  int8_t b_static;      /* 1: B is a constant (weights) — its tiles may be fetched before the kernel producing A ends */
+  int8_t _pad[4];
 } DfuGemmOperand;
 
 #define DFU_EPI_F32 0     /* out_f32[m, n] = v */
@@ -94,7 +95,7 @@ typedef struct DfuGemm {
   int32_t out_planes;      /* 1 or 2 */
   int64_t out_plane_stride;/* elements between planes */
   /* tiling (0 = choose automatically) */
-  int32_t block_n;         /* multiple of 32, <= 256, divides n */
+  int32_t block_n;         /* multiple of 16 (32 for GEGLU), <= 256, divides n */
   int32_t splits;          /* split-K factor */
   int32_t stages;
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
@@ -192,6 +193,17 @@ int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, co
                   const void* v, int ldv, int v_col0, int64_t kv_plane_stride, int B, int heads, int Nq, int Nk,
                   int planes, float scale, void* out, int ldo, int64_t out_plane_stride, int kv_splits,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- diagnostics --------------------------------------------------------------------------------
+ * In-kernel timeline records (one per CTA: grid id, kernel tag, SM, globaltimer / clock64 phase stamps) for
+ * scripts/trace_step.py.  `buf` = device u64 array: [0] next record (zeroed by the caller), [1] capacity in records,
+ * records of 12 u64 from [8]; NULL disables.  Only libdiffute_b200_trace.so (built with -DDFU_TRACE) records anything;
+ * in the product library these return -1 and no kernel contains tracing code.  One setter per translation unit.
+ */
+int dfu_trace_set_gemm(void* buf);
+int dfu_trace_set_attn(void* buf);
+int dfu_trace_set_norm(void* buf);
+int dfu_trace_set_misc(void* buf);
 
 #ifdef __cplusplus
 }
