@@ -84,12 +84,14 @@ __device__ __forceinline__ void store_f16x4(__half* dst, float4 v, bool lo_plane
 
 // (the epilogue is instruction-issue bound — ~2000 cycles per 32-column chunk round at 16 epilogue warps per SM, measured
 // with scripts/trace_step.py — so everything per-row is hoisted by the callers and alpha == 1 costs nothing)
-__device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, float4 v) {
+__device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, float4 v, const float* sbias = nullptr,
+                                             int n_tile0 = 0) {
   if (e.alpha != 1.0f) {
     v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
   }
   if (e.bias) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    const float4 t = sbias ? *reinterpret_cast<const float4*>(sbias + (n - n_tile0))
+                           : __ldg(reinterpret_cast<const float4*>(e.bias + n));
     v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
   if (e.rowvec) {
@@ -102,8 +104,9 @@ __device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, f
 }
 
 // residual already fetched by the caller (t = 0 when there is none)
-__device__ __forceinline__ void epi_quad_res(const EpiParams& e, int m, int n, float4 v, float4 t) {
-  v = epi_affine(e, m, n, v);
+__device__ __forceinline__ void epi_quad_res(const EpiParams& e, int m, int n, float4 v, float4 t,
+                                             const float* sbias = nullptr, int n_tile0 = 0) {
+  v = epi_affine(e, m, n, v, sbias, n_tile0);
   v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   if (e.epi == DFU_EPI_F32) {
     *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;
@@ -126,9 +129,10 @@ __device__ __forceinline__ void epi_quad(const EpiParams& e, int m, int n, float
 }
 
 // n_a = packed column of the value quad (the gate quad sits at n_a + 16); output column = block*16 + offset
-__device__ __forceinline__ void epi_geglu_quad(const EpiParams& e, int m, int n_a, float4 a, float4 g) {
-  a = epi_affine(e, m, n_a, a);
-  g = epi_affine(e, m, n_a + 16, g);
+__device__ __forceinline__ void epi_geglu_quad(const EpiParams& e, int m, int n_a, float4 a, float4 g,
+                                               const float* sbias = nullptr, int n_tile0 = 0) {
+  a = epi_affine(e, m, n_a, a, sbias, n_tile0);
+  g = epi_affine(e, m, n_a + 16, g, sbias, n_tile0);
   float4 o;
   o.x = a.x * gelu_erf_f(g.x); o.y = a.y * gelu_erf_f(g.y); o.z = a.z * gelu_erf_f(g.z); o.w = a.w * gelu_erf_f(g.w);
   const int n_out = (n_a >> 5) * 16 + (n_a & 15);
@@ -256,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[256];  // bias[n_tile0 .. n_tile0 + block_n)
 
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -425,8 +430,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool direct = p.splits == 1;
     const bool geglu = direct && p.e.epi == DFU_EPI_GEGLU;
     const bool has_res = direct && !geglu && p.e.residual != nullptr;
-    if (warp == 2 && p.e.bias != nullptr && lane * 8 < p.block_n)  // weights: before the wait (1 KiB = 32 sectors)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.e.bias + n_tile0 + lane * 8));
+    // the tile's bias slice is a weight: copied to shared memory before the wait (its first touch is an HBM miss)
+    if (warp == 2 && p.e.bias != nullptr && lane * 8 < p.block_n) {
+      *reinterpret_cast<float4*>(s_bias + lane * 8) = __ldg(reinterpret_cast<const float4*>(p.e.bias + n_tile0 + lane * 8));
+      *reinterpret_cast<float4*>(s_bias + lane * 8 + 4) = __ldg(reinterpret_cast<const float4*>(p.e.bias + n_tile0 + lane * 8 + 4));
+    }
     // the 32 rows of this warp are the same for every column chunk: (m, valid) of the rows this lane stores, once
     const int vmask = valid ? 1 : 0;
     int mrs[8];
@@ -439,6 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     const int cq = lane & 7;
     pdl_wait();  // residual / rowvec are activations, and the outputs may alias buffers earlier kernels still read
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // s_bias visible to the eight epilogue warps
     if (warp == 2 && p.e.rowvec != nullptr && lane * 8 < p.block_n)
       asm volatile("prefetch.global.L1 [%0];" ::"l"(p.e.rowvec + static_cast<size_t>((valid ? m : 0) / p.e.rows_per_sample) * p.e.rowvec_ld + n_tile0 + lane * 8));
     // residual quads are requested one chunk ahead (the first chunk's during the main loop): their L2 latency never
@@ -492,7 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int row = it * 8 + (lane >> 2), cq4 = lane & 3;
           const float4 a = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq4 * 4);
           const float4 g = *reinterpret_cast<const float4*>(stage + row * kStageLd + 16 + cq4 * 4);
-          if (mrs[it] >= 0) epi_geglu_quad(p.e, mrs[it], n + cq4 * 4, a, g);
+          if (mrs[it] >= 0) epi_geglu_quad(p.e, mrs[it], n + cq4 * 4, a, g, s_bias, n_tile0);
         }
       } else {
         const bool qok = cq * 4 < ncol;
@@ -504,7 +513,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (!direct)
               __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mrs[it]) * p.e.N + n + cq * 4), v);
             else
-              epi_quad_res(p.e, mrs[it], n + cq * 4, v, res[it]);
+              epi_quad_res(p.e, mrs[it], n + cq * 4, v, res[it], s_bias, n_tile0);
           }
           if (c + 64 < p.block_n) res[it] = fetch_res1(c + 64, it);
         }
@@ -672,10 +681,10 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
     if (stages > kb_cta) stages = kb_cta < 2 ? 2 : kb_cta;
   }
   if (stages > kMaxStages) stages = kMaxStages;
-  while (stages > 2 && stages * stage_bytes + 1024 > 226 * 1024) --stages;
+  while (stages > 2 && stages * stage_bytes + 1024 > 224 * 1024) --stages;
   pl->stages = stages;
   pl->smem_bytes = stages * stage_bytes + 1024;  // >= kStageBytes: the epilogue staging reuses the ring
-  DFU_REQUIRE(pl->smem_bytes <= 226 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
+  DFU_REQUIRE(pl->smem_bytes <= 224 * 1024, "gemm: smem %zu too large", pl->smem_bytes);
   return DFU_OK;
 }
 
@@ -792,7 +801,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;

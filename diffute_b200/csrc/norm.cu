@@ -302,6 +302,144 @@ __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(GnApply a) {
 }
 
 // =============================================================================================
+// Cluster GroupNorm: ONE launch, the input read ONCE, no grid-wide synchronisation.  The statistics of a group only
+// involve that group's channels, so the work is cut by CHANNELS first: a "unit" is the smallest run of groups whose
+// channel count is a multiple of 4 (1, 2 or 4 groups; q quads per pixel), and one thread-block cluster of S CTAs owns
+// one (sample, unit): CTA `rank` takes a slab of pixels, every thread keeps its <= ITEMS quads in registers, the
+// per-group sums are reduced warp -> CTA (shared memory, fixed order, double) -> cluster (distributed shared memory,
+// rank order) and the normalisation is applied from the registers.  Replaces gn_stats + gn_apply (two launches, two
+// reads, ~10 us per GroupNorm in the captured UNet step) wherever ITEMS <= 16 quads per thread fit.
+// =============================================================================================
+constexpr int kGnMaxU = 4;
+template <int ITEMS>
+__global__ void __launch_bounds__(512) gn_cluster_kernel(GnApply a, int U, int q, int TY, int S) {
+  pdl_trigger();
+  DFU_TR_BEGIN(TR_GN_FUSED);
+  __shared__ float s_w[16][kGnMaxU][2];
+  __shared__ __align__(16) double s_cta[kGnMaxU][2];
+  __shared__ float s_mean[kGnMaxU], s_rstd[kGnMaxU];
+  const int C = a.s.C0 + a.s.C1;
+  const int cpg = C / a.groups;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int unit = blockIdx.x / S;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int tx = tid % q, ty = tid / q;  // ty >= TY: spare threads of the last warp (no pixels, zero partials)
+  const int cq = unit * q + tx;
+  const int c = cq * 4;
+  int gs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gs[k] = (c + k) / cpg - unit * U;
+  // affine parameters are weights: fetched before waiting for the producer kernel
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  pdl_wait();
+  DFU_TR_MARK(6);
+  const int ppc = (a.s.HW + S - 1) / S;
+  const int p0 = rank * ppc;
+  const int p1 = min(p0 + ppc, a.s.HW);
+  float4 v[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int p = p0 + ty + i * TY;
+    v[i] = (ty < TY && p < p1) ? gn_load(a.s, b, p, cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float sx[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    sx[0] += v[i].x; sq[0] += v[i].x * v[i].x;
+    sx[1] += v[i].y; sq[1] += v[i].y * v[i].y;
+    sx[2] += v[i].z; sq[2] += v[i].z * v[i].z;
+    sx[3] += v[i].w; sq[3] += v[i].w * v[i].w;
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int u = 0; u < kGnMaxU; ++u) {
+    if (u < U) {  // uniform
+      float gsum = 0.f, gsq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (gs[k] == u) {
+          gsum += sx[k];
+          gsq += sq[k];
+        }
+      gsum = warp_sum(gsum);
+      gsq = warp_sum(gsq);
+      if (lane == 0) {
+        s_w[warp][u][0] = gsum;
+        s_w[warp][u][1] = gsq;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < U) {
+    double sd = 0.0, qd = 0.0;
+    for (int w = 0; w < nwarps; ++w) {
+      sd += s_w[w][tid][0];
+      qd += s_w[w][tid][1];
+    }
+    s_cta[tid][0] = sd;
+    s_cta[tid][1] = qd;
+  }
+  cluster_sync_all();  // every CTA's partial is in its shared memory
+  if (tid < U) {
+    double sd = 0.0, qd = 0.0;
+    const uint32_t loc = smem_u32(&s_cta[tid][0]);
+    double ps[8], pq[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {  // all remote loads in flight before the first add (S <= 8)
+      const uint32_t ra = dsmem_addr(loc, static_cast<uint32_t>(r < S ? r : 0));
+      ps[r] = ld_dsmem_f64(ra);
+      pq[r] = ld_dsmem_f64(ra + 8);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {  // rank order: deterministic
+      if (r < S) {
+        sd += ps[r];
+        qd += pq[r];
+      }
+    }
+    const double mean = sd / a.count;
+    double var = qd / a.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + a.eps));
+  }
+  cluster_arrive();  // "I have read my peers' partials"; the matching wait is the last statement of the kernel
+  __syncthreads();
+  DFU_TR_MARK(7);
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float be[4] = {be4.x, be4.y, be4.z, be4.w};
+  float mu[4], sc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mu[k] = s_mean[gs[k]];
+    sc[k] = s_rstd[gs[k]] * ga[k];
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int p = p0 + ty + i * TY;
+    if (ty < TY && p < p1) {
+      const float4 x = v[i];
+      float4 y;
+      y.x = (x.x - mu[0]) * sc[0] + be[0];
+      y.y = (x.y - mu[1]) * sc[1] + be[1];
+      y.z = (x.z - mu[2]) * sc[2] + be[2];
+      y.w = (x.w - mu[3]) * sc[3] + be[3];
+      if (a.silu) {
+        y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+      }
+      const size_t off = (static_cast<size_t>(b) * a.s.HW + p) * C + c;
+      if (a.out16) store_split4(a.out16 + off, a.plane_stride, a.planes, y);
+      if (a.out32) *reinterpret_cast<float4*>(a.out32 + off) = y;
+      if (a.raw16) store_split4(a.raw16 + off, a.plane_stride, a.planes, x);
+    }
+  }
+  DFU_TR_END();
+  cluster_wait();  // nobody leaves while a peer may still read its partial
+}
+
+// =============================================================================================
 // Fused GroupNorm: statistics + grid barrier + apply in ONE launch, the input read ONCE (each thread keeps its
 // <= 4 pixels x 4 channels in registers across the barrier).  Only for grids whose CTAs are all co-resident.
 // =============================================================================================
@@ -430,15 +568,15 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int C4 = C >> 2;
-  // gamma / beta are weights (they stream from HBM every step): pull them into L1 BEFORE waiting for the producer
-  // kernel, so that their latency overlaps its tail instead of sitting on the critical path after the reductions
-  // (a prefetch, not a register load: 80 more live registers would halve the occupancy)
-  if ((threadIdx.x >> 5) == 0) {
-    for (int o = lane * 32; o < C; o += 32 * 32) {  // one 128-byte line per lane and round
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(gamma + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(beta + o));
-    }
+  // gamma / beta are weights (they stream from HBM every step): copy them to shared memory BEFORE waiting for the
+  // producer kernel, so that their latency overlaps its tail instead of sitting on the critical path after the
+  // reductions (shared memory, not registers: 80 more live registers would halve the occupancy)
+  __shared__ __align__(16) float s_g[kLnMaxQuads * 128], s_b[kLnMaxQuads * 128];
+  for (int qd = threadIdx.x; qd < C4; qd += blockDim.x) {
+    reinterpret_cast<float4*>(s_g)[qd] = __ldg(reinterpret_cast<const float4*>(gamma) + qd);
+    reinterpret_cast<float4*>(s_b)[qd] = __ldg(reinterpret_cast<const float4*>(beta) + qd);
   }
+  __syncthreads();
   pdl_wait();
   DFU_TR_MARK(6);
   if (warp < M) {
@@ -470,8 +608,8 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
     for (int i = 0; i < kLnMaxQuads; ++i) {
       const int q = lane + 32 * i;
       if (q < C4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+        const float4 g = reinterpret_cast<const float4*>(s_g)[q];
+        const float4 b = reinterpret_cast<const float4*>(s_b)[q];
         float4 y;
         y.x = (v[i].x - mean) * rstd * g.x + b.x;
         y.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -559,6 +697,39 @@ static void gn_geometry(int B, int HW, int C, int* ty, int* ppc, int* chunks) {
   *chunks = nchunks(t);
 }
 
+// Number of S-CTA clusters of gn_cluster_kernel<...> (T threads) the device can hold at once; cached per (S, T, variant).
+static int gn_cluster_capacity(int S, int T, int variant) {
+  static int cache[4][17][3];  // [log2 S][T / 32][variant], 0 = unknown, -1 = query failed
+  int ls = 0;
+  while ((1 << ls) < S) ++ls;
+  const int ti = T / 32;
+  if (ls > 3 || ti > 16) return -1;
+  int& c = cache[ls][ti][variant];
+  if (c != 0) return c;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S * 64, 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(S);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e;
+  if (variant == 0) e = cudaOccupancyMaxActiveClusters(&n, gn_cluster_kernel<4>, &cfg);
+  else if (variant == 1) e = cudaOccupancyMaxActiveClusters(&n, gn_cluster_kernel<8>, &cfg);
+  else e = cudaOccupancyMaxActiveClusters(&n, gn_cluster_kernel<16>, &cfg);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = -1;
+  }
+  c = n > 0 ? n : -1;
+  return c;
+}
+
 extern "C" {
 
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups) {
@@ -586,6 +757,57 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   const int C4 = C / 4;
   dim3 block(C4, ty), grid(chunks, B);
   GnSrc s{src0, src1, C0, C1, HW};
+  // ---- single-launch cluster path (see gn_cluster_kernel) whenever <= 16 quads per thread fit ----
+  static const bool cluster_ok = !(getenv("DFU_GN_CLUSTER") && getenv("DFU_GN_CLUSTER")[0] == '0');
+  const int cpg = C / groups;
+  const int U = (cpg % 4 == 0) ? 1 : (cpg % 2 == 0 ? 2 : 4);
+  if (cluster_ok && groups % U == 0 && (U * cpg) % 4 == 0 && (U * cpg) / 4 <= 256) {
+    const int q = U * cpg / 4;
+    const int nunits = groups / U;
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    int bestS = 0, bestTY = 0, bestItems = 0;
+    double best = 1e30;
+    (void)sms;
+    for (int S = 8; S >= 1; S >>= 1) {
+      const int ppcS = (HW + S - 1) / S;
+      if (ppcS * (S - 1) >= HW && S > 1) continue;  // an empty rank
+      for (int T = 256; T <= 512; T += 256) {
+        const int TYc = T / q;
+        if (TYc < 1) continue;
+        const int items = (ppcS + TYc - 1) / TYc;
+        if (items > 16) continue;
+        const long long clusters = static_cast<long long>(nunits) * B;
+        // clusters that can be resident at once (GPC granularity: e.g. only ~16 clusters of 8 fit a B200)
+        const int cap = gn_cluster_capacity(S, ((q * TYc + 31) / 32) * 32, items <= 4 ? 0 : (items <= 8 ? 1 : 2));
+        if (cap <= 0) continue;
+        const double waves = static_cast<double>((clusters + cap - 1) / cap);
+        const double cost = waves * (items + 6) * (T == 512 ? 1.1 : 1.0);
+        if (cost < best) {
+          best = cost; bestS = S; bestTY = TYc; bestItems = items;
+        }
+      }
+    }
+    if (bestS > 0) {
+      GnApply f;
+      f.s = s; f.groups = groups; f.stats = nullptr; f.partial = nullptr; f.nchunks = 0; f.pix_per_cta = 0;
+      f.count = static_cast<double>(cpg) * HW;
+      f.gamma = gamma; f.beta = beta; f.eps = eps; f.silu = silu;
+      f.out16 = static_cast<__half*>(out16); f.planes = planes; f.plane_stride = plane_stride;
+      f.out32 = out32; f.raw16 = static_cast<__half*>(raw16);
+      const int T = ((q * bestTY + 31) / 32) * 32;
+      dim3 cgrid(bestS * nunits, B);
+      cudaError_t e;
+      if (bestItems <= 4)
+        e = launch_kc(gn_cluster_kernel<4>, cgrid, dim3(T), 0, stream, bestS, f, U, q, bestTY, bestS);
+      else if (bestItems <= 8)
+        e = launch_kc(gn_cluster_kernel<8>, cgrid, dim3(T), 0, stream, bestS, f, U, q, bestTY, bestS);
+      else
+        e = launch_kc(gn_cluster_kernel<16>, cgrid, dim3(T), 0, stream, bestS, f, U, q, bestTY, bestS);
+      DFU_CHECK_CUDA(e);
+      DFU_CHECK_CUDA(cudaGetLastError());
+      return DFU_OK;
+    }
+  }
   const size_t stats_smem = static_cast<size_t>(ty) * 2 * C * sizeof(float);
   // measured on B200 (in-graph, 64x64x320): fused 15.9 us vs stats+apply 12.3 us — the grid barrier costs more than
   // the launch it saves, so the single-launch variant is opt-in (DFU_GN_FUSED=1)

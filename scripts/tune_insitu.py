@@ -84,7 +84,7 @@ def candidates(s):
                 continue
             kb_cta = -(-s["kb"] // sp)
             st_half = max(2, min(kb_cta, (110 * 1024) // stage_b, 12))
-            st_full = max(2, min(kb_cta, (224 * 1024) // stage_b, 12))
+            st_full = max(2, min(kb_cta, (222 * 1024) // stage_b, 12))
             for st in sorted({st_half, st_full}):
                 out.append((bn, sp, st))
     # prune: drop configurations that leave most of the chip idle unless nothing else exists
