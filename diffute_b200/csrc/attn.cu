@@ -16,6 +16,13 @@
 //   warp 9    : tcgen05.mma issuer: S = Q K^T (K-major B), then O_blk = P V with V consumed MN-major straight
 //               from its natural [key, d] layout (no transpose pass).
 // In FP16X2 mode both contractions run as three passes over (hi, lo) operand planes.
+//
+// Work distribution ("stream-K" over key blocks): a work item is one (sample, head, 128-query tile) with nblk key blocks.
+// The items x nblk block-units are laid end to end and cut into G equal contiguous ranges, one per CTA, so a CTA runs
+// the tail of one item, possibly whole items, and the head of the next: with G = 2 x SMs every SM holds two equally
+// loaded CTAs whatever the (tile, head) count is (160 tiles on 148 SMs at 64x64 latents).  A range that covers a whole
+// item writes the result; partial ranges write (unnormalised O, row max, row sum) to the workspace and
+// attn_merge_kernel combines the pieces of an item in key order (deterministic).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -36,12 +43,19 @@ struct AttnParams {
   __half* out;      // [planes][B*Nq][ldo], head h at columns h*64
   int ldo;
   long long out_plane_stride;
-  // split-KV (flash-decoding style): blockIdx.z = b * kv_splits + s handles key blocks [s*bps, (s+1)*bps); partial
-  // (unnormalised O, row max, row sum) go to the workspace and attn_merge_kernel combines them
-  int kv_splits, blocks_per_split;
-  float* ws_o;      // [item][128][64] fp32, item = ((b*heads + head)*q_tiles + q_tile)*kv_splits + s
-  float* ws_ml;     // [item][128][2] (m in raw score units, l)
+  // stream-K distribution: CTA c owns block-units [c*total/G, (c+1)*total/G) of the items x nblk sequence
+  int q_tiles, nblk, items, G;
+  long long total;  // items * nblk
+  float* ws_o;      // [2*G slots][128][64] fp32; slot = 2*cta + (1 if the piece starts at its item's first block)
+  float* ws_ml;     // [2*G slots][128][2] (m in raw score units, l)
 };
+
+__host__ __device__ __forceinline__ long long attn_range_begin(const AttnParams& p, int c) {
+  return static_cast<long long>(c) * p.total / p.G;
+}
+__host__ __device__ __forceinline__ int attn_cta_of(const AttnParams& p, long long u) {  // CTA whose range holds unit u
+  return static_cast<int>(((u + 1) * p.G + p.total - 1) / p.total - 1);
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -53,7 +67,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   pdl_trigger();
-  DFU_TR_BEGIN(TR_ATTN | (p.kv_splits << 8));
+  DFU_TR_BEGIN(TR_ATTN | ((p.G > p.items ? 1 : 0) << 8));
   // No static shared memory: the dynamic window then starts 1024-byte aligned at the CTA's base, and the FP16 mode
   // needs 7 x 16 KiB + 128 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -74,17 +88,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t& p_full = bars[11];
   uint64_t& o_full = bars[12];
   uint64_t& o_free = bars[13];
-  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t& q_free = bars[14];  // all Q K^T MMAs of a segment have read Q: the next segment's Q may be loaded
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBQ;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z / p.kv_splits;
-  const int split = blockIdx.z % p.kv_splits;
-  const int nblk_all = (p.Nk + kBKV - 1) / kBKV;
-  const int jb0 = split * p.blocks_per_split;                       // first key block of this CTA
-  const int nblk = min(p.blocks_per_split, nblk_all - jb0);          // >= 1 by construction of kv_splits
+  const long long u_begin = attn_range_begin(p, blockIdx.x);
+  const long long u_end = attn_range_begin(p, blockIdx.x + 1);
+  if (u_begin >= u_end) return;  // (only when G > total; the host never launches that)
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -102,6 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(&p_full, kSoftmaxThreads);
     mbar_init(&o_full, 1);
     mbar_init(&o_free, kSoftmaxThreads);
+    mbar_init(&q_free, 1);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -119,23 +131,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_wait();
   DFU_TR_MARK(6);
 
+  // A segment = the part of one item inside this CTA's range: item index, first key block jb0, block count n.
+  // All three roles walk the same segment list; `g` counts key blocks over the whole range and keys every barrier
+  // parity and ring slot, so the pipeline runs straight through segment boundaries.
+  auto seg_of = [&](long long u, int& item, int& jb0, int& n) {
+    item = static_cast<int>(u / p.nblk);
+    jb0 = static_cast<int>(u - static_cast<long long>(item) * p.nblk);
+    const long long rest = u_end - u;
+    n = (p.nblk - jb0 < rest) ? p.nblk - jb0 : static_cast<int>(rest);
+  };
+  auto coords = [&](int item, int& b, int& head, int& q0) {
+    const int q_tile = item % p.q_tiles;
+    const int bh = item / p.q_tiles;
+    head = bh % p.heads;
+    b = bh / p.heads;
+    q0 = q_tile * kBQ;
+  };
+
   if (warp == 8) {
     // ===== TMA producer ======================================================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(&q_full, planes * kTile);
-      for (int pl = 0; pl < planes; ++pl)
-        tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
-      for (int j = 0; j < nblk; ++j) {
-        const int slot = j & 1;
-        const uint32_t par = ((j >> 1) & 1) ^ 1u;
-        mbar_wait(&k_empty[slot], par);
-        mbar_arrive_expect_tx(&k_full[slot], planes * kTile);
+      int g = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        int item, jb0, n, b, head, q0;
+        seg_of(u, item, jb0, n);
+        coords(item, b, head, q0);
+        if (seg > 0) mbar_wait(&q_free, (seg - 1) & 1);  // previous segment's Q K^T MMAs have all read Q
+        mbar_arrive_expect_tx(&q_full, planes * kTile);
         for (int pl = 0; pl < planes; ++pl)
-          tma_load_4d(sK + (slot * planes + pl) * kTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
-        mbar_wait(&v_empty[slot], par);
-        mbar_arrive_expect_tx(&v_full[slot], planes * kTile);
-        for (int pl = 0; pl < planes; ++pl)
-          tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+          tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
+        for (int j = 0; j < n; ++j, ++g) {
+          const int slot = g & 1;
+          const uint32_t par = ((g >> 1) & 1) ^ 1u;
+          mbar_wait(&k_empty[slot], par);
+          mbar_arrive_expect_tx(&k_full[slot], planes * kTile);
+          for (int pl = 0; pl < planes; ++pl)
+            tma_load_4d(sK + (slot * planes + pl) * kTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+          mbar_wait(&v_empty[slot], par);
+          mbar_arrive_expect_tx(&v_full[slot], planes * kTile);
+          for (int pl = 0; pl < planes; ++pl)
+            tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+        }
+        u += n;
       }
     }
   } else if (warp == 9) {
@@ -144,10 +181,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_qk = umma_idesc_f16(128, kBKV, 0);
       const uint32_t idesc_pv = umma_idesc_f16(128, kD, 1);  // B (= V) is MN-major
       const int npass = planes == 2 ? 3 : 1;
-      auto issue_qk = [&](int j) {
-        const int slot = j & 1;
-        mbar_wait(&k_full[slot], (j >> 1) & 1);
-        if (j > 0) mbar_wait(&s_free, (j - 1) & 1);
+      auto issue_qk = [&](int g, bool last_of_segment) {
+        const int slot = g & 1;
+        mbar_wait(&k_full[slot], (g >> 1) & 1);
+        if (g > 0) mbar_wait(&s_free, (g - 1) & 1);
         tc_fence_after();
         uint32_t acc = 0;
         for (int ps = 0; ps < npass; ++ps) {
@@ -162,31 +199,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         umma_commit(&s_full);
         umma_commit(&k_empty[slot]);
+        if (last_of_segment) umma_commit(&q_free);
       };
-      mbar_wait(&q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_qk(j + 1);
-        const int slot = j & 1;
-        mbar_wait(&p_full, j & 1);
-        mbar_wait(&v_full[slot], (j >> 1) & 1);
-        if (j > 0) mbar_wait(&o_free, (j - 1) & 1);
-        tc_fence_after();
-        uint32_t acc = 0;
-        for (int ps = 0; ps < npass; ++ps) {
-          const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
-          const uint32_t pbase = smem_u32(sP + pa * 2 * kTile);
-          const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kTile);
+      int g = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        int item, jb0, n;
+        seg_of(u, item, jb0, n);
+        mbar_wait(&q_full, seg & 1);
+        issue_qk(g, n == 1);
+        for (int j = 0; j < n; ++j, ++g) {
+          if (j + 1 < n) issue_qk(g + 1, j + 2 == n);
+          const int slot = g & 1;
+          mbar_wait(&p_full, g & 1);
+          mbar_wait(&v_full[slot], (g >> 1) & 1);
+          if (g > 0) mbar_wait(&o_free, (g - 1) & 1);
+          tc_fence_after();
+          uint32_t acc = 0;
+          for (int ps = 0; ps < npass; ++ps) {
+            const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
+            const uint32_t pbase = smem_u32(sP + pa * 2 * kTile);
+            const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kTile);
 #pragma unroll
-          for (int k = 0; k < kBKV / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(pbase + (k >> 2) * kTile) + 2 * (k & 3);
-            const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
-            umma_f16_ss(tmem_O, ad, bd, idesc_pv, acc);
-            acc = 1;
+            for (int k = 0; k < kBKV / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(pbase + (k >> 2) * kTile) + 2 * (k & 3);
+              const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
+              umma_f16_ss(tmem_O, ad, bd, idesc_pv, acc);
+              acc = 1;
+            }
           }
+          umma_commit(&o_full);
+          umma_commit(&v_empty[slot]);
         }
-        umma_commit(&o_full);
-        umma_commit(&v_empty[slot]);
+        u += n;
       }
     }
   } else {
@@ -194,144 +238,153 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int wg = warp >> 2;          // 0: key columns 0..63 / O columns 0..31; 1: the other halves
     const int r = threadIdx.x & 127;   // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     const float c2 = p.scale_log2;
     const uint32_t prow = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     uint8_t* tile_hi = sP + wg * kTile + prow;        // this warpgroup's 64 keys are exactly P tile `wg`
     uint8_t* tile_lo = sP + (2 + wg) * kTile + prow;
-
-    auto accumulate_o = [&](int j) {
-      mbar_wait(&o_full, j & 1);
-      tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld32(tmem_O + lane_off + wg * 32, raw);
-      tmem_ld_wait();
+    int g = 0;
+    for (long long u = u_begin; u < u_end;) {
+      int item, jb0, nblk, b, head, q0;
+      seg_of(u, item, jb0, nblk);
+      coords(item, b, head, q0);
+      float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+      float acc[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = acc[i] * alpha_prev + __uint_as_float(raw[i]);
-      tc_fence_before();
-      mbar_arrive(&o_free);
-    };
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full, j & 1);
-      tc_fence_after();
-      const int kv_valid = p.Nk - (jb0 + j) * kBKV - wg * 64;  // own columns >= kv_valid are padding
-      const bool full = kv_valid >= 64;                 // warp-uniform: interior blocks skip the tail predicates
-      // pass 1: max over the own 64 columns, then combine with the partner thread of the row
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      auto accumulate_o = [&](int gg) {
+        mbar_wait(&o_full, gg & 1);
+        tc_fence_after();
         uint32_t raw[32];
-        tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+        tmem_ld32(tmem_O + lane_off + wg * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (full || c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
-          mx = fmaxf(mx, v);
-        }
-      }
-      // exchange through two spare TMEM columns of the row's own lane (double-buffered by block parity): no shared
-      // memory, so two CTAs still fit one SM
-      const uint32_t xs = tmem_X + lane_off + (j & 1) * 2;
-      tmem_st1(xs + wg, __float_as_uint(mx));
-      tmem_st_wait();
-      tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      tc_fence_after();
-      const float other = __uint_as_float(tmem_ld1(xs + (wg ^ 1)));
-      tmem_ld_wait();
-      mx = fmaxf(m, fmaxf(mx, other));
-      const float alpha = fast_exp2((m - mx) * c2);  // first block: exp2(-inf) = 0
-      // the previous block's P*V must be finished before P is overwritten; fold its result in now
-      if (j > 0) accumulate_o(j - 1);
-      // pass 2: probabilities -> shared memory (swizzled K-major fp16), partial row sum
-      const float mc = mx * c2;
-      float rowsum = 0.f;
+        for (int i = 0; i < 32; ++i) acc[i] = acc[i] * alpha_prev + __uint_as_float(raw[i]);
+        tc_fence_before();
+        mbar_arrive(&o_free);
+      };
+
+      for (int j = 0; j < nblk; ++j, ++g) {
+        mbar_wait(&s_full, g & 1);
+        tc_fence_after();
+        const int kv_valid = p.Nk - (jb0 + j) * kBKV - wg * 64;  // own columns >= kv_valid are padding
+        const bool full = kv_valid >= 64;                 // warp-uniform: interior blocks skip the tail predicates
+        // pass 1: max over the own 64 columns, then combine with the partner thread of the row
+        float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
-        tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+          tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {  // 16-byte units of 8 probabilities
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int col = c * 32 + u * 8 + i;
-            const float e = fast_exp2(__uint_as_float(raw[u * 8 + i]) * c2 - mc);
-            pv[i] = (full || col < kv_valid) ? e : 0.f;
-            rowsum += pv[i];
+          for (int i = 0; i < 32; ++i) {
+            const float v = (full || c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
+            mx = fmaxf(mx, v);
           }
+        }
+        // exchange through two spare TMEM columns of the row's own lane (double-buffered by block parity): no shared
+        // memory, so two CTAs still fit one SM
+        const uint32_t xs = tmem_X + lane_off + (g & 1) * 2;
+        tmem_st1(xs + wg, __float_as_uint(mx));
+        tmem_st_wait();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        tc_fence_after();
+        const float other = __uint_as_float(tmem_ld1(xs + (wg ^ 1)));
+        tmem_ld_wait();
+        mx = fmaxf(m, fmaxf(mx, other));
+        const float alpha = fast_exp2((m - mx) * c2);  // first block: exp2(-inf) = 0
+        // the previous block's P*V must be finished before P is overwritten; fold its result in now
+        if (j > 0) accumulate_o(g - 1);
+        // pass 2: probabilities -> shared memory (swizzled K-major fp16), partial row sum
+        const float mc = mx * c2;
+        float rowsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) {  // 16-byte units of 8 probabilities
+            float pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int col = c * 32 + uu * 8 + i;
+              const float e = fast_exp2(__uint_as_float(raw[uu * 8 + i]) * c2 - mc);
+              pv[i] = (full || col < kv_valid) ? e : 0.f;
+              rowsum += pv[i];
+            }
+            __align__(16) __half2 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
+            const uint32_t unit = static_cast<uint32_t>(c * 4 + uu);
+            const uint32_t off = (unit ^ sw) << 4;
+            *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
+            if (planes == 2) {
+              __align__(16) __half2 lo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 hf = __half22float2(h[i]);
+                lo[i] = __floats2half2_rn(pv[2 * i] - hf.x, pv[2 * i + 1] - hf.y);
+              }
+              *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free);       // S may be overwritten by the next Q K^T
+        fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
+        mbar_arrive(&p_full);
+        l = l * alpha + rowsum;     // partial (own columns); both threads of a row apply the same alpha
+        m = mx;
+        alpha_prev = alpha;
+      }
+      accumulate_o(g - 1);
+      if (u + nblk >= u_end) DFU_TR_MARK(8);
+      // total row sum = partial(wg 0) + partial(wg 1), added in that order by both threads
+      {
+        const uint32_t xs = tmem_X + lane_off + (g & 1) * 2;
+        tmem_st1(xs + wg, __float_as_uint(l));
+        tmem_st_wait();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        tc_fence_after();
+        const float l0 = __uint_as_float(tmem_ld1(xs));
+        const float l1 = __uint_as_float(tmem_ld1(xs + 1));
+        tmem_ld_wait();
+        l = l0 + l1;
+      }
+      const int q = q0 + r;
+      if (nblk < p.nblk) {
+        // a piece of an item: unnormalised O and (m, l) to this CTA's slot (1 = the piece starts the item)
+        const size_t slot = static_cast<size_t>(blockIdx.x) * 2 + (jb0 == 0 ? 1 : 0);
+        float4* po = reinterpret_cast<float4*>(p.ws_o + (slot * 128 + r) * 64 + wg * 32);
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu)
+          __stcg(po + uu, make_float4(acc[4 * uu], acc[4 * uu + 1], acc[4 * uu + 2], acc[4 * uu + 3]));
+        if (wg == 0) __stcg(reinterpret_cast<float2*>(p.ws_ml + (slot * 128 + r) * 2), make_float2(m, l));
+      } else if (q < p.Nq) {
+        const float inv = 1.0f / l;
+        __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + wg * 32;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
           __align__(16) __half2 h[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
-          const uint32_t unit = static_cast<uint32_t>(c * 4 + u);
-          const uint32_t off = (unit ^ sw) << 4;
-          *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
+          for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(acc[uu * 8 + 2 * i] * inv, acc[uu * 8 + 2 * i + 1] * inv);
+          *reinterpret_cast<uint4*>(dst + uu * 8) = *reinterpret_cast<const uint4*>(h);
           if (planes == 2) {
             __align__(16) __half2 lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 hf = __half22float2(h[i]);
-              lo[i] = __floats2half2_rn(pv[2 * i] - hf.x, pv[2 * i + 1] - hf.y);
+              lo[i] = __floats2half2_rn(acc[uu * 8 + 2 * i] * inv - hf.x, acc[uu * 8 + 2 * i + 1] * inv - hf.y);
             }
-            *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(dst + p.out_plane_stride + uu * 8) = *reinterpret_cast<const uint4*>(lo);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&s_free);       // S may be overwritten by the next Q K^T
-      fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
-      mbar_arrive(&p_full);
-      l = l * alpha + rowsum;     // partial (own columns); both threads of a row apply the same alpha
-      m = mx;
-      alpha_prev = alpha;
-    }
-    accumulate_o(nblk - 1);
-    DFU_TR_MARK(8);
-    // total row sum = partial(wg 0) + partial(wg 1), added in that order by both threads
-    {
-      const uint32_t xs = tmem_X + lane_off + (nblk & 1) * 2;
-      tmem_st1(xs + wg, __float_as_uint(l));
-      tmem_st_wait();
-      tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      tc_fence_after();
-      const float l0 = __uint_as_float(tmem_ld1(xs));
-      const float l1 = __uint_as_float(tmem_ld1(xs + 1));
-      tmem_ld_wait();
-      l = l0 + l1;
-    }
-    const int q = q0 + r;
-    if (p.kv_splits > 1) {
-      const size_t item = ((static_cast<size_t>(b) * p.heads + head) * gridDim.x + blockIdx.x) * p.kv_splits + split;
-      float4* po = reinterpret_cast<float4*>(p.ws_o + (item * 128 + r) * 64 + wg * 32);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) __stcg(po + u, make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]));
-      if (wg == 0) __stcg(reinterpret_cast<float2*>(p.ws_ml + (item * 128 + r) * 2), make_float2(m, l));
-    } else if (q < p.Nq) {
-      const float inv = 1.0f / l;
-      __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + wg * 32;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        __align__(16) __half2 h[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(acc[u * 8 + 2 * i] * inv, acc[u * 8 + 2 * i + 1] * inv);
-        *reinterpret_cast<uint4*>(dst + u * 8) = *reinterpret_cast<const uint4*>(h);
-        if (planes == 2) {
-          __align__(16) __half2 lo[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 hf = __half22float2(h[i]);
-            lo[i] = __floats2half2_rn(acc[u * 8 + 2 * i] * inv - hf.x, acc[u * 8 + 2 * i + 1] * inv - hf.y);
-          }
-          *reinterpret_cast<uint4*>(dst + p.out_plane_stride + u * 8) = *reinterpret_cast<const uint4*>(lo);
-        }
-      }
+      u += nblk;
     }
   }
 
@@ -344,41 +397,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// Combine the kv_splits partial results of one (sample, head, query tile): O = sum_s O_s 2^((m_s - M) c2) / sum_s l_s
-// 2^((m_s - M) c2), slices in order (deterministic).  One 4-column quad per thread; every load of a thread (<= 8
-// slices x (m, l) + O quad) is issued before the first use, so the kernel costs one L2 round trip, not 2 x kv_splits.
+// Combine the pieces of every item that was cut across CTAs: O = sum_s O_s 2^((m_s - M) c2) / sum_s l_s 2^((m_s - M) c2),
+// pieces in key order (deterministic).  One 4-column quad per thread; every load of a thread (<= 8 pieces x ((m, l) +
+// O quad)) is issued before the first use, so the kernel costs one L2 round trip.  Items that one CTA covered
+// completely were written by attn_fwd_kernel and are skipped.
 constexpr int kMaxKvSplits = 8;
-__global__ void __launch_bounds__(256) attn_merge_kernel(AttnParams p, int q_tiles) {
+__global__ void __launch_bounds__(256) attn_merge_kernel(AttnParams p) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_ATTN_MERGE);
   pdl_wait();
   DFU_TR_MARK(6);
-  const int gidx = blockIdx.x * 256 + threadIdx.x;  // (tile, row, quad)
-  const int tile = gidx >> 11;                      // (b*heads + head)*q_tiles + q_tile
+  const int gidx = blockIdx.x * 256 + threadIdx.x;  // (item, row, quad)
+  const int item = gidx >> 11;
   const int r = (gidx >> 4) & 127, cq = gidx & 15;
-  const int q_tile = tile % q_tiles;
-  const int bh = tile / q_tiles;
+  const int q_tile = item % p.q_tiles;
+  const int bh = item / p.q_tiles;
   const int head = bh % p.heads, b = bh / p.heads;
   const int q = q_tile * kBQ + r;
-  if (q < p.Nq) {
-    const size_t item0 = static_cast<size_t>(tile) * p.kv_splits;
+  const long long u0 = static_cast<long long>(item) * p.nblk;
+  const int c_first = attn_cta_of(p, u0), c_last = attn_cta_of(p, u0 + p.nblk - 1);
+  const int pieces = c_last - c_first + 1;
+  if (q < p.Nq && pieces > 1) {
     float2 ml[kMaxKvSplits];
     float4 t[kMaxKvSplits];
 #pragma unroll
     for (int s = 0; s < kMaxKvSplits; ++s)
-      if (s < p.kv_splits) {
-        ml[s] = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + ((item0 + s) * 128 + r) * 2));
-        t[s] = __ldcg(reinterpret_cast<const float4*>(p.ws_o + ((item0 + s) * 128 + r) * 64 + cq * 4));
+      if (s < pieces) {
+        const int c = c_first + s;
+        const size_t slot = static_cast<size_t>(c) * 2 + (attn_range_begin(p, c) <= u0 ? 1 : 0);
+        ml[s] = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (slot * 128 + r) * 2));
+        t[s] = __ldcg(reinterpret_cast<const float4*>(p.ws_o + (slot * 128 + r) * 64 + cq * 4));
       }
     float M = -INFINITY;
 #pragma unroll
     for (int s = 0; s < kMaxKvSplits; ++s)
-      if (s < p.kv_splits) M = fmaxf(M, ml[s].x);
+      if (s < pieces) M = fmaxf(M, ml[s].x);
     float L = 0.f;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < kMaxKvSplits; ++s)
-      if (s < p.kv_splits) {
+      if (s < pieces) {
         const float w = fast_exp2((ml[s].x - M) * p.scale_log2);
         L += ml[s].y * w;
         o.x += t[s].x * w; o.y += t[s].y * w; o.z += t[s].z * w; o.w += t[s].w * w;
@@ -416,26 +474,40 @@ DFU_TRACE_SETTER(dfu_trace_set_attn)
 
 using namespace dfu;
 
-static int attn_auto_splits(int B, int heads, int Nq, int Nk) {
-  // One CTA alone on an SM is latency-bound (measured in the captured step: ~1.9-2.3 us per 128-key block alone,
-  // ~2.35 us each for two interleaved CTAs): when the (query tile, head) grid cannot put two CTAs on every SM, cut
-  // the key range so that it can.
+// Number of CTAs G for the stream-K distribution.  kv_splits > 0: items * kv_splits (an explicit even cut, 1 = no
+// cut); kv_splits <= 0: automatic.
+static int attn_grid(int B, int heads, int Nq, int Nk, int kv_splits) {
   const int q_tiles = (Nq + kBQ - 1) / kBQ;
   const int nblk = (Nk + kBKV - 1) / kBKV;
-  const int ctas = q_tiles * heads * B;
-  const int sms = num_sms() > 0 ? num_sms() : 148;
-  if (nblk < 4 || ctas >= 4 * sms) return 1;
-  int s = (4 * sms + ctas - 1) / ctas;
-  if (s > nblk / 2) s = nblk / 2;
-  if (s > kMaxKvSplits) s = kMaxKvSplits;
-  return s < 1 ? 1 : s;
+  const long long items = static_cast<long long>(q_tiles) * heads * B;
+  const long long total = items * nblk;
+  long long G;
+  if (kv_splits > 0) {
+    G = items * (kv_splits < nblk ? kv_splits : nblk);
+  } else {
+    // Measured in the captured UNet step (scripts/trace_step.py): a CTA alone on an SM is latency-bound (~1.9-2.3 us
+    // per 128-key block), two interleaved CTAs take ~2.35 us each, so the goal is two equally loaded CTAs per SM with
+    // at least two blocks each; many-item problems (>= 4 waves) balance by themselves and are not cut.
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    if (items >= 4LL * sms) {
+      G = items;
+    } else {
+      G = 2LL * sms;
+      if (G > total / 2) G = total / 2;
+      if (G < items) G = items;
+    }
+  }
+  if (G > items * 6) G = items * 6;  // <= 7 pieces per item (merge kernel holds 8)
+  if (G > total) G = total;
+  if (G < 1) G = 1;
+  return static_cast<int>(G);
 }
 
 extern "C" size_t dfu_attention_workspace(int B, int heads, int Nq, int Nk, int kv_splits) {
-  if (kv_splits <= 0) kv_splits = attn_auto_splits(B, heads, Nq, Nk);
-  if (kv_splits <= 1) return 0;
-  const size_t items = static_cast<size_t>(B) * heads * ((Nq + kBQ - 1) / kBQ) * kv_splits;
-  return items * (128 * 64 + 128 * 2) * sizeof(float);
+  const int q_tiles = (Nq + kBQ - 1) / kBQ;
+  const int G = attn_grid(B, heads, Nq, Nk, kv_splits);
+  if (G <= q_tiles * heads * B) return 0;  // every item inside one CTA's range: no partial pieces
+  return static_cast<size_t>(G) * 2 * (128 * 64 + 128 * 2) * sizeof(float);
 }
 
 extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, const void* k, int ldk,
@@ -458,26 +530,23 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   p.out = static_cast<__half*>(out);
   p.ldo = ldo;
   p.out_plane_stride = out_plane_stride;
-  const int nblk_all = (Nk + kBKV - 1) / kBKV;
-  if (kv_splits <= 0) kv_splits = attn_auto_splits(B, heads, Nq, Nk);
-  if (kv_splits > nblk_all) kv_splits = nblk_all;
-  DFU_REQUIRE(kv_splits <= kMaxKvSplits, "attention: kv_splits=%d > %d", kv_splits, kMaxKvSplits);
-  int bps = (nblk_all + kv_splits - 1) / kv_splits;
-  kv_splits = (nblk_all + bps - 1) / bps;  // no empty slices
-  p.kv_splits = kv_splits;
-  p.blocks_per_split = bps;
+  p.q_tiles = (Nq + kBQ - 1) / kBQ;
+  p.nblk = (Nk + kBKV - 1) / kBKV;
+  p.items = p.q_tiles * heads * B;
+  p.total = static_cast<long long>(p.items) * p.nblk;
+  p.G = attn_grid(B, heads, Nq, Nk, kv_splits);
   p.ws_o = nullptr;
   p.ws_ml = nullptr;
-  const int q_tiles = (Nq + kBQ - 1) / kBQ;
-  if (kv_splits > 1) {
-    const size_t items = static_cast<size_t>(B) * heads * q_tiles * kv_splits;
-    const size_t need = items * (128 * 64 + 128 * 2) * sizeof(float);
+  const bool pieces = p.G > p.items;
+  if (pieces) {
+    const size_t slots = static_cast<size_t>(p.G) * 2;
+    const size_t need = slots * (128 * 64 + 128 * 2) * sizeof(float);
     if (!workspace || workspace_bytes < need) {
-      set_error("attention: split-KV needs %zu workspace bytes, got %zu", need, workspace_bytes);
+      set_error("attention: cut key ranges need %zu workspace bytes, got %zu", need, workspace_bytes);
       return DFU_ERR_WORKSPACE;
     }
     p.ws_o = static_cast<float*>(workspace);
-    p.ws_ml = p.ws_o + items * 128 * 64;
+    p.ws_ml = p.ws_o + slots * 128 * 64;
   }
   const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 128;
   static bool attr = false;
@@ -485,9 +554,8 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
     DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  dim3 grid(q_tiles, heads, B * kv_splits);
-  DFU_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream_), mQ, mK, mV, p));
-  if (kv_splits > 1)
-    DFU_CHECK_CUDA(launch_k(attn_merge_kernel, dim3(B * heads * q_tiles * 8), dim3(256), 0, static_cast<cudaStream_t>(stream_), p, q_tiles));
+  DFU_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(p.G), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream_), mQ, mK, mV, p));
+  if (pieces)
+    DFU_CHECK_CUDA(launch_k(attn_merge_kernel, dim3(p.items * 8), dim3(256), 0, static_cast<cudaStream_t>(stream_), p));
   return DFU_OK;
 }

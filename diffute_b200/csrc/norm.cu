@@ -768,6 +768,7 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
     int bestS = 0, bestTY = 0, bestItems = 0;
     double best = 1e30;
     (void)sms;
+    static const int max_items = getenv("DFU_GN_MAX_ITEMS") ? atoi(getenv("DFU_GN_MAX_ITEMS")) : 16;
     for (int S = 8; S >= 1; S >>= 1) {
       const int ppcS = (HW + S - 1) / S;
       if (ppcS * (S - 1) >= HW && S > 1) continue;  // an empty rank
@@ -775,7 +776,7 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
         const int TYc = T / q;
         if (TYc < 1) continue;
         const int items = (ppcS + TYc - 1) / TYc;
-        if (items > 16) continue;
+        if (items > max_items) continue;
         const long long clusters = static_cast<long long>(nunits) * B;
         // clusters that can be resident at once (GPC granularity: e.g. only ~16 clusters of 8 fit a B200)
         const int cap = gn_cluster_capacity(S, ((q * TYc + 31) / 32) * 32, items <= 4 ? 0 : (items <= 8 ? 1 : 2));
@@ -784,6 +785,16 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
         const double cost = waves * (items + 6) * (T == 512 ? 1.1 : 1.0);
         if (cost < best) {
           best = cost; bestS = S; bestTY = TYc; bestItems = items;
+        }
+      }
+    }
+    if (const char* force = getenv("DFU_GN_FORCE")) {  // diagnostics: "S,T" overrides the choice (scripts/bench_gn.py)
+      int fs = 0, ft = 0;
+      if (sscanf(force, "%d,%d", &fs, &ft) == 2 && fs >= 1 && ft >= 32) {
+        const int ppcS = (HW + fs - 1) / fs;
+        const int TYc = ft / q;
+        if (TYc >= 1 && (ppcS + TYc - 1) / TYc <= 16) {
+          bestS = fs; bestTY = TYc; bestItems = (ppcS + TYc - 1) / TYc;
         }
       }
     }

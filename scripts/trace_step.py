@@ -118,5 +118,18 @@ print("\nper kernel class: launches, sum gap us, sum body us")
 for k, a in sorted(agg.items(), key=lambda kv: -(kv[1][1] + kv[1][2])):
     print(f"  {k:14} {a[0]:4d} {a[1]:8.1f} {a[2]:8.1f}")
 os.makedirs("gpurun_out", exist_ok=True)
+if os.environ.get("TRACE_DUMP"):
+    # raw per-CTA records of the n-th launch of one kernel class: TRACE_DUMP=attn:0
+    kname, nth = os.environ["TRACE_DUMP"].split(":")
+    gids = [d["grid_id"] for d in rows if d["kernel"] == kname]
+    gid = gids[int(nth)]
+    raw = trace._buf[8:8 + int(trace._buf[0].item()) * trace.REC].view(-1, trace.REC).cpu().numpy()
+    sel = raw[raw[:, 0] == gid]
+    t0 = sel[:, 3].min()
+    out = [{"bid": int(r[1] >> 32), "smid": int(r[2] & 0xFFFFFFFF), "start": (int(r[3]) - int(t0)) / 1e3,
+            "marks": [(int(r[i]) - int(r[4])) / 1965.0 if r[i] else None for i in range(5, 11)],
+            "end": (int(r[11]) - int(t0)) / 1e3} for r in sel]
+    with open("gpurun_out/trace_dump.json", "w") as f:
+        json.dump(out, f)
 with open("gpurun_out/trace_step.json", "w") as f:
     json.dump({"step_us": step_ms * 1e3, "launches": rows}, f)

@@ -44,9 +44,14 @@ def test_attention(ops, planes, B, heads, Nq, Nk, fused):
     out16 = torch.zeros((planes, B * Nq, C), dtype=torch.float16, device="cuda")
     ops.attention(q16, cols[0], k16, cols[1], v16, cols[2], B, heads, Nq, Nk, scale, out16)
     torch.cuda.synchronize()
-    # forced split-KV (2 and 3 key slices + merge kernel) must agree with the automatic choice
+    # deterministic: the stream-K cut and the in-order merge give the same bits on every run
+    o1 = torch.zeros_like(out16)
+    ops.attention(q16, cols[0], k16, cols[1], v16, cols[2], B, heads, Nq, Nk, scale, o1)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, out16)
+    # forced cuts (no cut; 2, 3 and 5 CTAs per item + merge kernel) must agree with the automatic distribution
     if Nk > 256:
-        for ks in (2, 3):
+        for ks in (1, 2, 3, 5):
             o2 = torch.zeros_like(out16)
             ops.attention(q16, cols[0], k16, cols[1], v16, cols[2], B, heads, Nq, Nk, scale, o2, kv_splits=ks)
             torch.cuda.synchronize()
