@@ -145,6 +145,8 @@ constexpr int kStageFloats = 32 * kStageLd;           // per epilogue warp
 // split-K second stage: every thread owns one output quad, sums the `splits` fp32 partials in slice order
 // (deterministic), four independent 16-byte loads in flight at a time, then runs the fused epilogue.
 __device__ __forceinline__ float4 sum_partials(const float* __restrict__ src, size_t plane, int splits) {
+  // four independent 16-byte loads in flight per thread, summed in slice order.  (Eight in flight was measured slower:
+  // the register cost halves the occupancy of this latency-bound kernel — 231 vs 206 us per UNet step.)
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   int s = 0;
   for (; s + 4 <= splits; s += 4) {
@@ -446,6 +448,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mrs[it] = vr ? mr : -1;
     }
     const int cq = lane & 7;
+    // sample index of the warp's rows (time-embedding row of the epilogue): uniform in all but tiny feature maps
+    int smp0 = 0;
+    bool one_sample = true;
+    if (p.e.rowvec != nullptr) {
+      const int smp = valid ? m / p.e.rows_per_sample : -1;
+      smp0 = __reduce_max_sync(0xffffffffu, smp);
+      one_sample = __all_sync(0xffffffffu, smp < 0 || smp == smp0);
+      if (smp0 < 0) smp0 = 0;
+    }
     pdl_wait();  // residual / rowvec are activations, and the outputs may alias buffers earlier kernels still read
     asm volatile("bar.sync 1, 256;" ::: "memory");  // s_bias visible to the eight epilogue warps
     if (warp == 2 && p.e.rowvec != nullptr && lane * 8 < p.block_n)
@@ -495,7 +506,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         __uint_as_float(raw[4 * i + 3]));
       __syncwarp();
       const int n = n_tile0 + c;
-      if (geglu) {
+      // per-chunk constants of this lane's column quad(s): bias (+ the time-embedding row when the warp's rows belong
+      // to one sample) are added with one FFMA per element; nothing per-row is recomputed inside the loops
+      const float alpha = p.e.alpha;
+      if (geglu && p.e.rowvec == nullptr) {
+        const int cq4 = lane & 3;
+        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+        if (p.e.bias) {
+          ba = *reinterpret_cast<const float4*>(s_bias + c + cq4 * 4);
+          bg = *reinterpret_cast<const float4*>(s_bias + c + 16 + cq4 * 4);
+        }
+        const int n_out = ((n + cq4 * 4) >> 5) * 16 + ((n + cq4 * 4) & 15);
+        const bool lo_plane = p.e.out_planes > 1;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + (lane >> 2);
+          const float4 a = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq4 * 4);
+          const float4 g = *reinterpret_cast<const float4*>(stage + row * kStageLd + 16 + cq4 * 4);
+          if (mrs[it] >= 0) {
+            float4 o;
+            o.x = fmaf(a.x, alpha, ba.x) * gelu_erf_f(fmaf(g.x, alpha, bg.x));
+            o.y = fmaf(a.y, alpha, ba.y) * gelu_erf_f(fmaf(g.y, alpha, bg.y));
+            o.z = fmaf(a.z, alpha, ba.z) * gelu_erf_f(fmaf(g.z, alpha, bg.z));
+            o.w = fmaf(a.w, alpha, ba.w) * gelu_erf_f(fmaf(g.w, alpha, bg.w));
+            store_f16x4(p.e.out_f16 + static_cast<size_t>(mrs[it]) * p.e.ldh + n_out, o, lo_plane, p.e.out_plane_stride);
+          }
+        }
+      } else if (geglu) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int row = it * 8 + (lane >> 2), cq4 = lane & 3;
@@ -503,36 +540,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const float4 g = *reinterpret_cast<const float4*>(stage + row * kStageLd + 16 + cq4 * 4);
           if (mrs[it] >= 0) epi_geglu_quad(p.e, mrs[it], n + cq4 * 4, a, g, s_bias, n_tile0);
         }
-      } else {
+      } else if (!direct) {
         const bool qok = cq * 4 < ncol;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
           const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
+          if (qok && mrs[it] >= 0)
+            __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mrs[it]) * p.e.N + n + cq * 4), v);
+        }
+      } else {
+        const bool qok = cq * 4 < ncol;
+        float4 aq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qok && p.e.bias) aq = *reinterpret_cast<const float4*>(s_bias + c + cq * 4);
+        if (qok && p.e.rowvec && one_sample) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.e.rowvec + static_cast<size_t>(smp0) * p.e.rowvec_ld + n + cq * 4));
+          aq.x += t.x; aq.y += t.y; aq.z += t.z; aq.w += t.w;
+        }
+        const bool per_row_vec = p.e.rowvec != nullptr && !one_sample;
+        const bool f32_out = p.e.epi == DFU_EPI_F32;
+        const bool lo_plane = p.e.out_planes > 1;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3);
+          const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageLd + cq * 4);
           if (qok && mrs[it] >= 0) {
-            if (!direct)
-              __stcg(reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.e.M + mrs[it]) * p.e.N + n + cq * 4), v);
+            float4 o;
+            o.x = fmaf(v.x, alpha, aq.x) + res[it].x;
+            o.y = fmaf(v.y, alpha, aq.y) + res[it].y;
+            o.z = fmaf(v.z, alpha, aq.z) + res[it].z;
+            o.w = fmaf(v.w, alpha, aq.w) + res[it].w;
+            if (per_row_vec) {  // a warp whose rows span two samples (tiny feature maps): the row's own vector
+              const float4 t = __ldg(reinterpret_cast<const float4*>(
+                  p.e.rowvec + static_cast<size_t>(mrs[it] / p.e.rows_per_sample) * p.e.rowvec_ld + n + cq * 4));
+              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            if (f32_out)
+              *reinterpret_cast<float4*>(p.e.out_f32 + static_cast<size_t>(mrs[it]) * p.e.ldo + n + cq * 4) = o;
             else
-              epi_quad_res(p.e, mrs[it], n + cq * 4, v, res[it], s_bias, n_tile0);
+              store_f16x4(p.e.out_f16 + static_cast<size_t>(mrs[it]) * p.e.ldh + n + cq * 4, o, lo_plane, p.e.out_plane_stride);
           }
           if (c + 64 < p.block_n) res[it] = fetch_res1(c + 64, it);
         }
       }
     }
     if (threadIdx.x == 64) DFU_TR_SHARED_MARK(9);
-    if (p.splits > 1 && p.sync != nullptr) {
-      // Fused second stage (all CTAs of this launch are co-resident): once every slice has parked its partial tile
-      // in the L2-resident workspace, the epilogue threads of ALL CTAs share the reduction + fused epilogue, one
-      // output quad at a time — the same arithmetic and order as splitk_reduce_kernel, without a second launch.
-      __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 64) grid_barrier(p.sync, gridDim.x);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const long long total = static_cast<long long>(p.e.M) * (p.e.epi == DFU_EPI_GEGLU ? p.e.N / 8 : p.e.N / 4);
-      for (long long idx = static_cast<long long>(blockIdx.x) * kEpiThreads + (threadIdx.x - 64); idx < total;
-           idx += static_cast<long long>(gridDim.x) * kEpiThreads)
-        reduce_quad(p.ws, p.splits, p.e, idx);
-    }
   }
 
   if (p.cluster > 1) {
@@ -812,20 +864,9 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     const size_t part = static_cast<size_t>(kBlockM) * (pl.block_n + 4) * 4;
     if (part <= pl.smem_bytes - 1024) p.cluster = pl.splits;
   }
+  // (a grid-barrier variant of the second stage was built and measured on B200: the barrier, ~4-5 us, cost more than
+  // the PDL-overlapped reduce launch it saved, so it is gone; `sync_words` is accepted and ignored)
   p.sync = nullptr;
-  // measured on B200: a grid barrier (~4-5 us) costs more than the second launch it saves (~2.5 us with PDL),
-  // so the fused second stage is opt-in (DFU_SPLITK_FUSED=1)
-  static const bool fused_ok = getenv("DFU_SPLITK_FUSED") && getenv("DFU_SPLITK_FUSED")[0] == '1';
-  if (pl.splits > 1 && !p.cluster && d->sync_words && fused_ok) {
-    int per_sm = 0;
-    DFU_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_tc_kernel, kGemmThreads, pl.smem_bytes));
-    const int tmem_limit = 512 / static_cast<int>(p.tmem_cols);
-    if (per_sm > tmem_limit) per_sm = tmem_limit;
-    const int sms = num_sms() > 0 ? num_sms() : 148;
-    if (grid <= per_sm * sms) p.sync = reinterpret_cast<unsigned int*>(d->sync_words);
-    g_stats[4] = per_sm;
-    g_stats[5] = grid;
-  }
   g_stats[0]++;
   if (pl.splits > 1) g_stats[1]++;
   if (p.sync) g_stats[2]++;
