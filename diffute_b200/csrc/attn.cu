@@ -239,6 +239,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = threadIdx.x & 127;   // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c2 = p.scale_log2;
+    const uint32_t pair_bar = 1u + static_cast<uint32_t>(warp & 3);  // named barrier of warps (w, w + 4)
     const uint32_t prow = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     uint8_t* tile_hi = sP + wg * kTile + prow;        // this warpgroup's 64 keys are exactly P tile `wg`
@@ -289,7 +290,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st1(xs + wg, __float_as_uint(mx));
         tmem_st_wait();
         tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // only the two warps that share these 32 rows
         tc_fence_after();
         const float other = __uint_as_float(tmem_ld1(xs + (wg ^ 1)));
         tmem_ld_wait();
@@ -348,7 +349,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st1(xs + wg, __float_as_uint(l));
         tmem_st_wait();
         tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // only the two warps that share these 32 rows
         tc_fence_after();
         const float l0 = __uint_as_float(tmem_ld1(xs));
         const float l1 = __uint_as_float(tmem_ld1(xs + 1));
@@ -489,7 +490,9 @@ static int attn_grid(int B, int heads, int Nq, int Nk, int kv_splits) {
     // per 128-key block), two interleaved CTAs take ~2.35 us each, so the goal is two equally loaded CTAs per SM with
     // at least two blocks each; many-item problems (>= 4 waves) balance by themselves and are not cut.
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    if (items >= 4LL * sms) {
+    if (items >= 4LL * sms || nblk < 8) {
+      // short key sequences (the 577 glyph tokens = 5 blocks): the merge launch (~6-8 us) costs more than the
+      // imbalance it removes (measured: 18.6 us uncut vs 18.5 + 8.0 us cut at 160 tiles x 5 blocks)
       G = items;
     } else {
       G = 2LL * sms;

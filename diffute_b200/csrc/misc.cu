@@ -96,25 +96,32 @@ struct SmallInSrc {
   int nhwc;              // 1: sources are NHWC [B,H,W,c] instead of NCHW
 };
 
-constexpr int kSmallInPix = 16;  // output pixels per CTA
+constexpr int kSmallInPix = 32;  // output pixels per CTA
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const float* __restrict__ wt,
                      const float* __restrict__ bias, int Cout, float pre_scale, float* __restrict__ out) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_CONV_IN);
-  pdl_wait();
-  DFU_TR_MARK(6);
-  // block: kSmallInPix consecutive output pixels x all Cout; input patches staged in smem; weights are stored
-  // [Cin*k*k][Cout] so that consecutive lanes (consecutive output channels) read consecutive addresses.
-  extern __shared__ float sm[];  // [kSmallInPix][K]
+  // block: kSmallInPix consecutive output pixels x all Cout (one thread per output channel: coalesced NHWC stores);
+  // input patches staged in smem as [K][pixel] so that four pixels come with one 16-byte broadcast read; weights are
+  // stored [Cin*k*k][Cout] so that consecutive lanes read consecutive addresses.
+  extern __shared__ __align__(16) float sm[];  // [K][kSmallInPix]
   const int kk = ksz * ksz;
   const int K = Cin * kk;
   const int pad = ksz / 2;
+  const int co = threadIdx.x;
+  // the first nine taps' weights and the bias are constants: requested before waiting for the producer of the input
+  float wv[9];
+#pragma unroll
+  for (int u = 0; u < 9; ++u) wv[u] = (co < Cout && u < K) ? __ldg(wt + static_cast<size_t>(u) * Cout + co) : 0.f;
+  const float b0 = (bias && co < Cout) ? __ldg(bias + co) : 0.f;
+  pdl_wait();
+  DFU_TR_MARK(6);
   const long long pix0 = static_cast<long long>(blockIdx.x) * kSmallInPix;
   const long long npix = static_cast<long long>(B) * H * W;
   for (int i = threadIdx.x; i < kSmallInPix * K; i += blockDim.x) {
-    const int pl = i / K, k = i % K;
+    const int k = i / kSmallInPix, pl = i % kSmallInPix;  // consecutive threads -> consecutive pixels (coalesced NCHW)
     const long long pix = pix0 + pl;
     float v = 0.f;
     if (pix < npix) {
@@ -135,28 +142,38 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
     sm[i] = v;
   }
   __syncthreads();
-  // thread -> output channel co (fastest, coalesced NHWC stores) for a strip of pixels
-  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+  if (co < Cout) {
     float acc[kSmallInPix];
-    const float b0 = bias ? bias[co] : 0.f;
 #pragma unroll
     for (int j = 0; j < kSmallInPix; ++j) acc[j] = b0;
-    for (int k0 = 0; k0 < K; k0 += 9) {  // weights fetched nine at a time: one L2 latency per tap group, not per tap
-      float wv[9];
+    for (int k0 = 0; k0 < K; k0 += 9) {
+      // the next nine weights are requested before this group's FMAs: their L2 latency hides behind ~300 instructions
+      float wn[9];
 #pragma unroll
-      for (int u = 0; u < 9; ++u) wv[u] = (k0 + u < K) ? __ldg(wt + static_cast<size_t>(k0 + u) * Cout + co) : 0.f;
+      for (int u = 0; u < 9; ++u)
+        wn[u] = (k0 + 9 + u < K) ? __ldg(wt + static_cast<size_t>(k0 + 9 + u) * Cout + co) : 0.f;
 #pragma unroll
       for (int u = 0; u < 9; ++u) {
         if (k0 + u < K) {
+          const float4* row = reinterpret_cast<const float4*>(sm + (k0 + u) * kSmallInPix);
 #pragma unroll
-          for (int j = 0; j < kSmallInPix; ++j) acc[j] += wv[u] * sm[j * K + k0 + u];
+          for (int j4 = 0; j4 < kSmallInPix / 4; ++j4) {
+            const float4 x = row[j4];
+            acc[4 * j4 + 0] = fmaf(wv[u], x.x, acc[4 * j4 + 0]);
+            acc[4 * j4 + 1] = fmaf(wv[u], x.y, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(wv[u], x.z, acc[4 * j4 + 2]);
+            acc[4 * j4 + 3] = fmaf(wv[u], x.w, acc[4 * j4 + 3]);
+          }
         }
       }
+#pragma unroll
+      for (int u = 0; u < 9; ++u) wv[u] = wn[u];
     }
 #pragma unroll
     for (int j = 0; j < kSmallInPix; ++j)
       if (pix0 + j < npix) out[(pix0 + j) * Cout + co] = acc[j];
   }
+  DFU_TR_END();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,7 +456,9 @@ int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* 
   const long long npix = static_cast<long long>(B) * H * W;
   const int blocks = static_cast<int>((npix + kSmallInPix - 1) / kSmallInPix);
   const size_t smem = static_cast<size_t>(kSmallInPix) * Cin * ksz * ksz * sizeof(float);
-  DFU_CHECK_CUDA(launch_k(conv_small_in_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream), s, B, H, W, Cin, ksz, w, bias, Cout, pre_scale, out));
+  DFU_REQUIRE(Cout >= 1 && Cout <= 512, "conv_small_in: Cout=%d (one thread per output channel, max 512)", Cout);
+  const int threads = ((Cout + 31) / 32) * 32;
+  DFU_CHECK_CUDA(launch_k(conv_small_in_kernel, dim3(blocks), dim3(threads), smem, static_cast<cudaStream_t>(stream), s, B, H, W, Cin, ksz, w, bias, Cout, pre_scale, out));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
