@@ -4,17 +4,19 @@
 // 577 glyph tokens) in BasicTransformerBlock — SURVEY.md A.1, reached from app.ipynb:814.
 //
 // One CTA = 128 query rows of one (sample, head); it streams K/V in blocks of 128 keys:
-//   warps 0-7 : two softmax warpgroups.  Thread (wg, r) owns query row r (= TMEM lane r) for the 64 key columns
-//               [64*wg, 64*wg+64) of each S block and the 32 output columns [32*wg, 32*wg+32) of O: the exp / convert
-//               work per block — the binding resource of this kernel (MUFU + issue slots) — is spread over 8 warps.
-//               The two threads of a row exchange their partial row max through shared memory once per block.
-//               S is read from TMEM with tcgen05.ld, P is written to shared memory as fp16 (hi [, lo]) in the
-//               128-byte-swizzled K-major layout the next MMA consumes; O is accumulated in registers with the
-//               online-softmax rescale.
+//   warps 0-7 : two INDEPENDENT softmax warpgroups.  Thread (wg, r) owns query row r (= TMEM lane r) for the 64 key
+//               columns [64*wg, 64*wg+64) of every S block, with its own running reference max, row sum and its own
+//               accumulator O_wg in TMEM (O_wg += P_wg V[64*wg:64*wg+64]): nothing is exchanged per block — no
+//               barrier, no second reader of S — and the two halves of a row are merged once per work item
+//               (O = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1), w = 2^((m - max m) c)).  The reference max is lazy
+//               (FlashAttention-4 style): it only moves when the block max exceeds it by more than 2^8 in the exp2
+//               domain, and only then is O_wg rescaled in TMEM (tcgen05.ld / st), so the common block costs two reads
+//               of S, 64 ex2 and the fp16 P tile.  S is read from TMEM with tcgen05.ld, P is written to shared memory
+//               as fp16 (hi [, lo]) in the 128-byte-swizzled K-major layout the next MMA consumes.
 //   warp 8    : TMA producer (Q once; K and V double-buffered rings; 4-D maps so rows past the sequence end are
 //               zero-filled per sample and per plane).
-//   warp 9    : tcgen05.mma issuer: S = Q K^T (K-major B), then O_blk = P V with V consumed MN-major straight
-//               from its natural [key, d] layout (no transpose pass).
+//   warp 9    : tcgen05.mma issuer: S = Q K^T (K-major B), then per half O_wg += P_wg V_wg with V consumed MN-major
+//               straight from its natural [key, d] layout (no transpose pass).
 // In FP16X2 mode both contractions run as three passes over (hi, lo) operand planes.
 //
 // Work distribution ("stream-K" over key blocks): a work item is one (sample, head, 128-query tile) with nblk key blocks.
@@ -69,7 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_trigger();
   DFU_TR_BEGIN(TR_ATTN | ((p.G > p.items ? 1 : 0) << 8));
   // No static shared memory: the dynamic window then starts 1024-byte aligned at the CTA's base, and the FP16 mode
-  // needs 7 x 16 KiB + 128 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
+  // needs 7 x 16 KiB + 192 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
   extern __shared__ __align__(1024) uint8_t smem[];
   const int planes = p.planes;
   // layout: Q[planes] | K[2][planes] | V[2][planes] | P[planes][2 tiles] | barriers
@@ -85,11 +87,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* v_empty = bars + 7;
   uint64_t& s_full = bars[9];
   uint64_t& s_free = bars[10];
-  uint64_t& p_full = bars[11];
-  uint64_t& o_full = bars[12];
-  uint64_t& o_free = bars[13];
-  uint64_t& q_free = bars[14];  // all Q K^T MMAs of a segment have read Q: the next segment's Q may be loaded
-  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_full = bars + 11;  // [2] one per softmax warpgroup (128 arrivals)
+  uint64_t* o_full = bars + 13;  // [2] P_wg V_wg of a block has completed
+  uint64_t& o_free = bars[15];   // both accumulators of a finished segment have been read (256 arrivals)
+  uint64_t& q_free = bars[16];   // all Q K^T MMAs of a segment have read Q: the next segment's Q may be loaded
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,8 +112,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     mbar_init(&s_full, 1);
     mbar_init(&s_free, kSoftmaxThreads);
-    mbar_init(&p_full, kSoftmaxThreads);
-    mbar_init(&o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], kSoftmaxThreads / 2);
+      mbar_init(&o_full[i], 1);
+    }
     mbar_init(&o_free, kSoftmaxThreads);
     mbar_init(&q_free, 1);
     fence_mbar_init();
@@ -125,8 +129,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_S = tmem_base;        // 128 columns
-  const uint32_t tmem_O = tmem_base + 128;  // 64 columns
-  const uint32_t tmem_X = tmem_base + 192;  // 4 spare columns: per-row exchange between the two softmax warpgroups
+  const uint32_t tmem_O = tmem_base + 128;  // 2 x 64 columns: O_0, O_1
   DFU_TR_MARK(5);
   pdl_wait();
   DFU_TR_MARK(6);
@@ -210,24 +213,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int j = 0; j < n; ++j, ++g) {
           if (j + 1 < n) issue_qk(g + 1, j + 2 == n);
           const int slot = g & 1;
-          mbar_wait(&p_full, g & 1);
           mbar_wait(&v_full[slot], (g >> 1) & 1);
-          if (g > 0) mbar_wait(&o_free, (g - 1) & 1);
-          tc_fence_after();
-          uint32_t acc = 0;
-          for (int ps = 0; ps < npass; ++ps) {
-            const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
-            const uint32_t pbase = smem_u32(sP + pa * 2 * kTile);
-            const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kTile);
+          if (j == 0 && seg > 0) mbar_wait(&o_free, (seg - 1) & 1);  // the previous item's accumulators were read
 #pragma unroll
-            for (int k = 0; k < kBKV / 16; ++k) {
-              const uint64_t ad = umma_desc_sw128(pbase + (k >> 2) * kTile) + 2 * (k & 3);
-              const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
-              umma_f16_ss(tmem_O, ad, bd, idesc_pv, acc);
-              acc = 1;
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&p_full[h], g & 1);
+            tc_fence_after();
+            uint32_t acc = j > 0 ? 1u : 0u;  // O_h accumulates in TMEM over the blocks of a segment
+            for (int ps = 0; ps < npass; ++ps) {
+              const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
+              const uint32_t pbase = smem_u32(sP + (pa * 2 + h) * kTile);
+              const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kTile) + (4 * h) * 2048;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = umma_desc_sw128(pbase) + 2 * k;
+                const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
+                umma_f16_ss(tmem_O + 64 * h, ad, bd, idesc_pv, acc);
+                acc = 1;
+              }
             }
+            umma_commit(&o_full[h]);
           }
-          umma_commit(&o_full);
           umma_commit(&v_empty[slot]);
         }
         u += n;
@@ -235,138 +241,164 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ===== softmax warpgroups (warps 0..7) ======================================================
-    const int wg = warp >> 2;          // 0: key columns 0..63 / O columns 0..31; 1: the other halves
+    const int wg = warp >> 2;          // key columns [64*wg, 64*wg+64) of every block; output columns [32*wg, 32*wg+32)
     const int r = threadIdx.x & 127;   // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c2 = p.scale_log2;
+    const float lazy = 8.0f / c2;      // the reference max moves only when exceeded by 2^8 in the exp2 domain
     const uint32_t pair_bar = 1u + static_cast<uint32_t>(warp & 3);  // named barrier of warps (w, w + 4)
     const uint32_t prow = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     uint8_t* tile_hi = sP + wg * kTile + prow;        // this warpgroup's 64 keys are exactly P tile `wg`
     uint8_t* tile_lo = sP + (2 + wg) * kTile + prow;
+    const uint32_t tmem_Oown = tmem_O + 64 * wg + lane_off;
     int g = 0;
     for (long long u = u_begin; u < u_end;) {
       int item, jb0, nblk, b, head, q0;
       seg_of(u, item, jb0, nblk);
       coords(item, b, head, q0);
-      float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-      float acc[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-
-      auto accumulate_o = [&](int gg) {
-        mbar_wait(&o_full, gg & 1);
-        tc_fence_after();
-        uint32_t raw[32];
-        tmem_ld32(tmem_O + lane_off + wg * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = acc[i] * alpha_prev + __uint_as_float(raw[i]);
-        tc_fence_before();
-        mbar_arrive(&o_free);
-      };
+      float m = -INFINITY, l = 0.f;   // reference max (raw score units) and row sum at that reference, own columns
 
       for (int j = 0; j < nblk; ++j, ++g) {
         mbar_wait(&s_full, g & 1);
         tc_fence_after();
         const int kv_valid = p.Nk - (jb0 + j) * kBKV - wg * 64;  // own columns >= kv_valid are padding
         const bool full = kv_valid >= 64;                 // warp-uniform: interior blocks skip the tail predicates
-        // pass 1: max over the own 64 columns, then combine with the partner thread of the row
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = (full || c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
-            mx = fmaxf(mx, v);
-          }
+        // P_wg V_wg of the previous block must be finished before the P tile is overwritten (and before O_wg is
+        // touched); it was issued a whole softmax block ago, so this does not stall
+        if (j > 0) {
+          mbar_wait(&o_full[wg], (g - 1) & 1);
+          tc_fence_after();
         }
-        // exchange through two spare TMEM columns of the row's own lane (double-buffered by block parity): no shared
-        // memory, so two CTAs still fit one SM
-        const uint32_t xs = tmem_X + lane_off + (g & 1) * 2;
-        tmem_st1(xs + wg, __float_as_uint(mx));
-        tmem_st_wait();
-        tc_fence_before();
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // only the two warps that share these 32 rows
-        tc_fence_after();
-        const float other = __uint_as_float(tmem_ld1(xs + (wg ^ 1)));
-        tmem_ld_wait();
-        mx = fmaxf(m, fmaxf(mx, other));
-        const float alpha = fast_exp2((m - mx) * c2);  // first block: exp2(-inf) = 0
-        // the previous block's P*V must be finished before P is overwritten; fold its result in now
-        if (j > 0) accumulate_o(g - 1);
-        // pass 2: probabilities -> shared memory (swizzled K-major fp16), partial row sum
-        const float mc = mx * c2;
+        if (j == 0) {
+          // first block of a segment: the reference is its exact max (one extra read of S per ~17 blocks)
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = (full || c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
+              mx = fmaxf(mx, v);
+            }
+          }
+          m = mx;
+        }
+        // ONE pass over S in the common case (TMEM reads bound this kernel): probabilities are computed against the
+        // current reference while the block max is tracked; only if some row of the warp outgrew the 2^8 headroom is
+        // O_wg rescaled and the block redone against the new reference (S is still there: s_free not yet signalled).
         float rowsum = 0.f;
+        for (int attempt = 0;; ++attempt) {
+          const float mc = (m == -INFINITY) ? 0.f : m * c2;
+          float mx = -INFINITY;
+          rowsum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
-          tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+            tmem_ld_wait();
+            if (!full) {  // ragged last block only (warp-uniform): padding columns become -inf -> probability 0
 #pragma unroll
-          for (int uu = 0; uu < 4; ++uu) {  // 16-byte units of 8 probabilities
-            float pv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int col = c * 32 + uu * 8 + i;
-              const float e = fast_exp2(__uint_as_float(raw[uu * 8 + i]) * c2 - mc);
-              pv[i] = (full || col < kv_valid) ? e : 0.f;
-              rowsum += pv[i];
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= kv_valid) raw[i] = 0xff800000u;
             }
-            __align__(16) __half2 h[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
-            const uint32_t unit = static_cast<uint32_t>(c * 4 + uu);
-            const uint32_t off = (unit ^ sw) << 4;
-            *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
-            if (planes == 2) {
-              __align__(16) __half2 lo[4];
+            for (int uu = 0; uu < 4; ++uu) {  // 16-byte units of 8 probabilities
+              float pv[8];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 hf = __half22float2(h[i]);
-                lo[i] = __floats2half2_rn(pv[2 * i] - hf.x, pv[2 * i + 1] - hf.y);
+              for (int i = 0; i < 8; ++i) pv[i] = __uint_as_float(raw[uu * 8 + i]);
+              // short dependency chains: a tree per unit, one add / max per unit into the running values
+              const float um = fmaxf(fmaxf(fmaxf(pv[0], pv[1]), fmaxf(pv[2], pv[3])),
+                                     fmaxf(fmaxf(pv[4], pv[5]), fmaxf(pv[6], pv[7])));
+              mx = fmaxf(mx, um);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(pv[i] * c2 - mc);
+              rowsum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+              __align__(16) __half2 h[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
+              const uint32_t unit = static_cast<uint32_t>(c * 4 + uu);
+              const uint32_t off = (unit ^ sw) << 4;
+              *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
+              if (planes == 2) {
+                __align__(16) __half2 lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 hf = __half22float2(h[i]);
+                  lo[i] = __floats2half2_rn(pv[2 * i] - hf.x, pv[2 * i + 1] - hf.y);
+                }
+                *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
               }
-              *reinterpret_cast<uint4*>(tile_lo + off) = *reinterpret_cast<const uint4*>(lo);
             }
+          }
+          if (j == 0 || attempt == 1) break;
+          const bool move = mx > m + lazy;  // (m == -inf: any valid score moves it)
+          if (!__any_sync(0xffffffffu, move)) break;
+          // tcgen05.ld / st are warp-collective: every lane takes part, rows that stay use alpha = 1
+          const float alpha = move ? fast_exp2((m - mx) * c2) : 1.f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_Oown + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+            tmem_st32(tmem_Oown + c * 32, raw);
+          }
+          tmem_st_wait();
+          if (move) {
+            l *= alpha;
+            m = mx;
           }
         }
         tc_fence_before();
         mbar_arrive(&s_free);       // S may be overwritten by the next Q K^T
         fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
-        mbar_arrive(&p_full);
-        l = l * alpha + rowsum;     // partial (own columns); both threads of a row apply the same alpha
-        m = mx;
-        alpha_prev = alpha;
+        mbar_arrive(&p_full[wg]);
+        l += rowsum;
       }
-      accumulate_o(g - 1);
+      // ---- end of the segment: merge the two halves of every row ----
+      mbar_wait(&o_full[0], (g - 1) & 1);
+      mbar_wait(&o_full[1], (g - 1) & 1);
+      tc_fence_after();
       if (u + nblk >= u_end) DFU_TR_MARK(8);
-      // total row sum = partial(wg 0) + partial(wg 1), added in that order by both threads
+      // (m, l) of the partner thread of the row through the first 8 bytes of the (now idle) P tile rows
+      *reinterpret_cast<float2*>(tile_hi) = make_float2(m, l);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // only the two warps that share these 32 rows
+      const float2 other = *reinterpret_cast<const float2*>(sP + (wg ^ 1) * kTile + prow);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both have read before either rewrites its tile
+      const float m0 = wg == 0 ? m : other.x, m1 = wg == 0 ? other.x : m;
+      const float l0 = wg == 0 ? l : other.y, l1 = wg == 0 ? other.y : l;
+      const float M = fmaxf(m0, m1);   // finite: every row has at least one valid key in the segment
+      const float w0 = fast_exp2((m0 - M) * c2), w1 = fast_exp2((m1 - M) * c2);  // a half without valid keys: 0
+      const float L = l0 * w0 + l1 * w1;
+      float acc[32];
       {
-        const uint32_t xs = tmem_X + lane_off + (g & 1) * 2;
-        tmem_st1(xs + wg, __float_as_uint(l));
-        tmem_st_wait();
-        tc_fence_before();
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // only the two warps that share these 32 rows
-        tc_fence_after();
-        const float l0 = __uint_as_float(tmem_ld1(xs));
-        const float l1 = __uint_as_float(tmem_ld1(xs + 1));
+        uint32_t raw[32];
+        tmem_ld32(tmem_O + lane_off + wg * 32, raw);
         tmem_ld_wait();
-        l = l0 + l1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(raw[i]) * w0;
+        tmem_ld32(tmem_O + 64 + lane_off + wg * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = fmaf(__uint_as_float(raw[i]), w1, acc[i]);
       }
+      tc_fence_before();
+      mbar_arrive(&o_free);  // the next segment's first P V may overwrite the accumulators
       const int q = q0 + r;
       if (nblk < p.nblk) {
-        // a piece of an item: unnormalised O and (m, l) to this CTA's slot (1 = the piece starts the item)
+        // a piece of an item: unnormalised O and (M, L) to this CTA's slot (1 = the piece starts the item)
         const size_t slot = static_cast<size_t>(blockIdx.x) * 2 + (jb0 == 0 ? 1 : 0);
         float4* po = reinterpret_cast<float4*>(p.ws_o + (slot * 128 + r) * 64 + wg * 32);
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu)
           __stcg(po + uu, make_float4(acc[4 * uu], acc[4 * uu + 1], acc[4 * uu + 2], acc[4 * uu + 3]));
-        if (wg == 0) __stcg(reinterpret_cast<float2*>(p.ws_ml + (slot * 128 + r) * 2), make_float2(m, l));
+        if (wg == 0) __stcg(reinterpret_cast<float2*>(p.ws_ml + (slot * 128 + r) * 2), make_float2(M, L));
       } else if (q < p.Nq) {
-        const float inv = 1.0f / l;
+        const float inv = 1.0f / L;
         __half* dst = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * kD + wg * 32;
 #pragma unroll
         for (int uu = 0; uu < 4; ++uu) {
@@ -551,7 +583,7 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
     p.ws_o = static_cast<float*>(workspace);
     p.ws_ml = p.ws_o + slots * 128 * 64;
   }
-  const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 128;
+  const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 192;
   static bool attr = false;
   if (!attr) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
