@@ -3,19 +3,21 @@
 // Replaces diffusers' Attention core (attn1 self-attention over H*W tokens and attn2 cross-attention over the
 // 577 glyph tokens) in BasicTransformerBlock — SURVEY.md A.1, reached from app.ipynb:814.
 //
-// One CTA = 128 query rows of one (sample, head); it streams K/V in blocks of 128 keys:
-//   warps 0-7 : two INDEPENDENT softmax warpgroups.  Thread (wg, r) owns query row r (= TMEM lane r) for the 64 key
-//               columns [64*wg, 64*wg+64) of every S block, with its own running reference max, row sum and its own
-//               accumulator O_wg in TMEM (O_wg += P_wg V[64*wg:64*wg+64]): nothing is exchanged per block — no
-//               barrier, no second reader of S — and the two halves of a row are merged once per work item
-//               (O = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1), w = 2^((m - max m) c)).  The reference max is lazy
-//               (FlashAttention-4 style): it only moves when the block max exceeds it by more than 2^8 in the exp2
-//               domain, and only then is O_wg rescaled in TMEM (tcgen05.ld / st), so the common block costs two reads
-//               of S, 64 ex2 and the fp16 P tile.  S is read from TMEM with tcgen05.ld, P is written to shared memory
-//               as fp16 (hi [, lo]) in the 128-byte-swizzled K-major layout the next MMA consumes.
-//   warp 8    : TMA producer (Q once; K and V double-buffered rings; 4-D maps so rows past the sequence end are
-//               zero-filled per sample and per plane).
-//   warp 9    : tcgen05.mma issuer: S = Q K^T (K-major B), then per half O_wg += P_wg V_wg with V consumed MN-major
+// One CTA = 128 query rows of one (sample, head); it streams K/V in blocks of 64 keys:
+//   warps 0-7 : two softmax warpgroups that take ALTERNATE key blocks (block g belongs to warpgroup g & 1).  Each has
+//               its own S buffer (64 TMEM columns), P tile and accumulator O_wg in TMEM, its own running reference
+//               max and row sum: while one warpgroup exponentiates block g, the tensor core already computes
+//               S(g+1) for the other — the Q K^T round trip that starved a single shared S buffer (ncu: the softmax
+//               warps sat on the S barrier) is off the critical path, and nothing is exchanged per block.  Thread
+//               (wg, r) owns query row r (= TMEM lane r) of its blocks; the two partial results of a row are merged
+//               once per work item (O = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1), w = 2^((m - max m) c)).  The
+//               reference max is lazy (FlashAttention-4 style): probabilities are computed against the current
+//               reference in ONE pass over S while the block max is tracked; only when a row outgrows 2^8 of headroom
+//               is O_wg rescaled in TMEM (tcgen05.ld / st) and the block redone.  P is written to shared memory as fp16
+//               (hi [, lo]) in the 128-byte-swizzled K-major layout the P V MMA consumes.
+//   warp 8    : TMA producer (Q once per work item; K and V in 4-deep rings of 64-key tiles; 4-D maps so rows past
+//               the sequence end are zero-filled per sample and per plane).
+//   warp 9    : tcgen05.mma issuer: S_wg = Q K^T (K-major B) two blocks ahead, O_wg += P_wg V with V consumed MN-major
 //               straight from its natural [key, d] layout (no transpose pass).
 // In FP16X2 mode both contractions run as three passes over (hi, lo) operand planes.
 //
@@ -33,9 +35,11 @@ namespace dfu {
 constexpr int kAttnThreads = 320;
 constexpr int kSoftmaxThreads = 256;
 constexpr int kBQ = 128;    // queries per CTA
-constexpr int kBKV = 128;   // keys per block
+constexpr int kBKV = 64;    // keys per block
+constexpr int kRing = 4;    // K / V ring depth (tiles of 64 keys)
 constexpr int kD = 64;
-constexpr uint32_t kTile = 128 * 128;  // bytes of one [128 rows x 64 halfs] swizzled tile
+constexpr uint32_t kTile = 128 * 128;  // bytes of one [128 rows x 64 halfs] swizzled tile (Q, P)
+constexpr uint32_t kKvTile = 64 * 128;  // bytes of one [64 keys x 64 halfs] swizzled tile (K, V)
 
 struct AttnParams {
   int B, heads, Nq, Nk;
@@ -71,27 +75,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_trigger();
   DFU_TR_BEGIN(TR_ATTN | ((p.G > p.items ? 1 : 0) << 8));
   // No static shared memory: the dynamic window then starts 1024-byte aligned at the CTA's base, and the FP16 mode
-  // needs 7 x 16 KiB + 192 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
+  // needs 7 x 16 KiB + 256 B, so two CTAs fit one SM (one's softmax overlaps the other's MMAs).
   extern __shared__ __align__(1024) uint8_t smem[];
   const int planes = p.planes;
-  // layout: Q[planes] | K[2][planes] | V[2][planes] | P[planes][2 tiles] | barriers
+  // layout: Q[planes] | K[kRing][planes] | V[kRing][planes] | P[planes][2 warpgroups] | barriers
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + planes * kTile;
-  uint8_t* sV = sK + 2 * planes * kTile;
-  uint8_t* sP = sV + 2 * planes * kTile;
+  uint8_t* sV = sK + kRing * planes * kKvTile;
+  uint8_t* sP = sV + kRing * planes * kKvTile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * planes * kTile);
   uint64_t& q_full = bars[0];
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 7;
-  uint64_t& s_full = bars[9];
-  uint64_t& s_free = bars[10];
-  uint64_t* p_full = bars + 11;  // [2] one per softmax warpgroup (128 arrivals)
-  uint64_t* o_full = bars + 13;  // [2] P_wg V_wg of a block has completed
-  uint64_t& o_free = bars[15];   // both accumulators of a finished segment have been read (256 arrivals)
-  uint64_t& q_free = bars[16];   // all Q K^T MMAs of a segment have read Q: the next segment's Q may be loaded
-  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t& q_free = bars[1];    // all Q K^T MMAs of a segment have read Q: the next segment's Q may be loaded
+  uint64_t* k_full = bars + 2;   // [kRing]
+  uint64_t* k_empty = bars + 6;
+  uint64_t* v_full = bars + 10;
+  uint64_t* v_empty = bars + 14;
+  uint64_t* s_full = bars + 18;  // [2] per warpgroup: its S buffer holds a new block
+  uint64_t* s_free = bars + 20;  // [2] 128 arrivals: the warpgroup has read its S buffer
+  uint64_t* p_full = bars + 22;  // [2] 128 arrivals: the warpgroup's P tile is written
+  uint64_t* o_full = bars + 24;  // [2] P_wg V of a block has completed
+  uint64_t& o_free = bars[26];   // 256 arrivals: both accumulators of a finished segment have been read
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,20 +108,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(&q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(&q_free, 1);
+    for (int i = 0; i < kRing; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(&s_full, 1);
-    mbar_init(&s_free, kSoftmaxThreads);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], kSoftmaxThreads / 2);
       mbar_init(&p_full[i], kSoftmaxThreads / 2);
       mbar_init(&o_full[i], 1);
     }
     mbar_init(&o_free, kSoftmaxThreads);
-    mbar_init(&q_free, 1);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -128,7 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t tmem_S = tmem_base;        // 128 columns
+  const uint32_t tmem_S = tmem_base;        // 2 x 64 columns: S_0, S_1
   const uint32_t tmem_O = tmem_base + 128;  // 2 x 64 columns: O_0, O_1
   DFU_TR_MARK(5);
   pdl_wait();
@@ -164,16 +168,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int pl = 0; pl < planes; ++pl)
           tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
         for (int j = 0; j < n; ++j, ++g) {
-          const int slot = g & 1;
-          const uint32_t par = ((g >> 1) & 1) ^ 1u;
+          const int slot = g % kRing;
+          const uint32_t par = ((g / kRing) & 1) ^ 1u;
           mbar_wait(&k_empty[slot], par);
-          mbar_arrive_expect_tx(&k_full[slot], planes * kTile);
+          mbar_arrive_expect_tx(&k_full[slot], planes * kKvTile);
           for (int pl = 0; pl < planes; ++pl)
-            tma_load_4d(sK + (slot * planes + pl) * kTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+            tma_load_4d(sK + (slot * planes + pl) * kKvTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
           mbar_wait(&v_empty[slot], par);
-          mbar_arrive_expect_tx(&v_full[slot], planes * kTile);
+          mbar_arrive_expect_tx(&v_full[slot], planes * kKvTile);
           for (int pl = 0; pl < planes; ++pl)
-            tma_load_4d(sV + (slot * planes + pl) * kTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+            tma_load_4d(sV + (slot * planes + pl) * kKvTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
         }
         u += n;
       }
@@ -184,23 +188,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_qk = umma_idesc_f16(128, kBKV, 0);
       const uint32_t idesc_pv = umma_idesc_f16(128, kD, 1);  // B (= V) is MN-major
       const int npass = planes == 2 ? 3 : 1;
-      auto issue_qk = [&](int g, bool last_of_segment) {
-        const int slot = g & 1;
-        mbar_wait(&k_full[slot], (g >> 1) & 1);
-        if (g > 0) mbar_wait(&s_free, (g - 1) & 1);
+      // block gg belongs to warpgroup h = gg & 1 and is that warpgroup's (gg >> 1)-th block
+      auto issue_qk = [&](int gg, bool last_of_segment) {
+        const int slot = gg % kRing, h = gg & 1, c = gg >> 1;
+        mbar_wait(&k_full[slot], (gg / kRing) & 1);
+        if (c > 0) mbar_wait(&s_free[h], (c - 1) & 1);  // the warpgroup has read its previous block out of S_h
         tc_fence_after();
         uint32_t acc = 0;
         for (int ps = 0; ps < npass; ++ps) {
           const int qa = (ps == 1) ? 1 : 0, kb = (ps == 2) ? 1 : 0;
           const uint64_t ad = umma_desc_sw128(smem_u32(sQ + qa * kTile));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sK + (slot * planes + kb) * kTile));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sK + (slot * planes + kb) * kKvTile));
 #pragma unroll
           for (int k = 0; k < kD / 16; ++k) {
-            umma_f16_ss(tmem_S, ad + 2 * k, bd + 2 * k, idesc_qk, acc);
+            umma_f16_ss(tmem_S + 64 * h, ad + 2 * k, bd + 2 * k, idesc_qk, acc);
             acc = 1;
           }
         }
-        umma_commit(&s_full);
+        umma_commit(&s_full[h]);
         umma_commit(&k_empty[slot]);
         if (last_of_segment) umma_commit(&q_free);
       };
@@ -209,39 +214,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         int item, jb0, n;
         seg_of(u, item, jb0, n);
         mbar_wait(&q_full, seg & 1);
-        issue_qk(g, n == 1);
-        for (int j = 0; j < n; ++j, ++g) {
-          if (j + 1 < n) issue_qk(g + 1, j + 2 == n);
-          const int slot = g & 1;
-          mbar_wait(&v_full[slot], (g >> 1) & 1);
+        issue_qk(g, n == 1);            // S two blocks ahead of the P V: both warpgroups have work from the start
+        if (n > 1) issue_qk(g + 1, n == 2);
+        for (int j = 0; j < n; ++j) {
+          const int gg = g + j, slot = gg % kRing, h = gg & 1, c = gg >> 1;
+          mbar_wait(&v_full[slot], (gg / kRing) & 1);
           if (j == 0 && seg > 0) mbar_wait(&o_free, (seg - 1) & 1);  // the previous item's accumulators were read
+          mbar_wait(&p_full[h], c & 1);
+          tc_fence_after();
+          uint32_t acc = j >= 2 ? 1u : 0u;  // O_h accumulates in TMEM over the warpgroup's blocks of a segment
+          for (int ps = 0; ps < npass; ++ps) {
+            const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
+            const uint32_t pbase = smem_u32(sP + (pa * 2 + h) * kTile);
+            const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kKvTile);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(&p_full[h], g & 1);
-            tc_fence_after();
-            uint32_t acc = j > 0 ? 1u : 0u;  // O_h accumulates in TMEM over the blocks of a segment
-            for (int ps = 0; ps < npass; ++ps) {
-              const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
-              const uint32_t pbase = smem_u32(sP + (pa * 2 + h) * kTile);
-              const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kTile) + (4 * h) * 2048;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = umma_desc_sw128(pbase) + 2 * k;
-                const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
-                umma_f16_ss(tmem_O + 64 * h, ad, bd, idesc_pv, acc);
-                acc = 1;
-              }
+            for (int k = 0; k < kBKV / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(pbase) + 2 * k;
+              const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
+              umma_f16_ss(tmem_O + 64 * h, ad, bd, idesc_pv, acc);
+              acc = 1;
             }
-            umma_commit(&o_full[h]);
           }
+          umma_commit(&o_full[h]);
           umma_commit(&v_empty[slot]);
+          if (j + 2 < n) issue_qk(gg + 2, j + 3 == n);
         }
+        g += n;
         u += n;
       }
     }
   } else {
     // ===== softmax warpgroups (warps 0..7) ======================================================
-    const int wg = warp >> 2;          // key columns [64*wg, 64*wg+64) of every block; output columns [32*wg, 32*wg+32)
+    const int wg = warp >> 2;          // takes the key blocks gg with (gg & 1) == wg; output columns [32*wg, 32*wg+32)
     const int r = threadIdx.x & 127;   // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c2 = p.scale_log2;
@@ -249,60 +253,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t pair_bar = 1u + static_cast<uint32_t>(warp & 3);  // named barrier of warps (w, w + 4)
     const uint32_t prow = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    uint8_t* tile_hi = sP + wg * kTile + prow;        // this warpgroup's 64 keys are exactly P tile `wg`
+    uint8_t* tile_hi = sP + wg * kTile + prow;        // P tile of this warpgroup (hi plane), own row
     uint8_t* tile_lo = sP + (2 + wg) * kTile + prow;
+    const uint32_t tmem_Sown = tmem_S + 64 * wg + lane_off;
     const uint32_t tmem_Oown = tmem_O + 64 * wg + lane_off;
     int g = 0;
     for (long long u = u_begin; u < u_end;) {
       int item, jb0, nblk, b, head, q0;
       seg_of(u, item, jb0, nblk);
       coords(item, b, head, q0);
-      float m = -INFINITY, l = 0.f;   // reference max (raw score units) and row sum at that reference, own columns
-
-      for (int j = 0; j < nblk; ++j, ++g) {
-        mbar_wait(&s_full, g & 1);
+      float m = -INFINITY, l = 0.f;   // reference max (raw score units) and row sum at that reference, own blocks
+      int nown = 0;                   // own blocks of this segment done so far
+      int c = 0;
+      for (int gg = g + ((g & 1) != wg ? 1 : 0); gg < g + nblk; gg += 2, ++nown) {
+        c = gg >> 1;                  // this warpgroup's block counter over the whole range
+        mbar_wait(&s_full[wg], c & 1);
         tc_fence_after();
-        const int kv_valid = p.Nk - (jb0 + j) * kBKV - wg * 64;  // own columns >= kv_valid are padding
-        const bool full = kv_valid >= 64;                 // warp-uniform: interior blocks skip the tail predicates
-        // P_wg V_wg of the previous block must be finished before the P tile is overwritten (and before O_wg is
-        // touched); it was issued a whole softmax block ago, so this does not stall
-        if (j > 0) {
-          mbar_wait(&o_full[wg], (g - 1) & 1);
+        const int kv_valid = p.Nk - (jb0 + (gg - g)) * kBKV;  // columns >= kv_valid are padding
+        const bool full = kv_valid >= kBKV;                   // warp-uniform: interior blocks skip the tail predicates
+        // P_wg V of the previous own block must be finished before the P tile is overwritten (and before O_wg is
+        // touched); it was issued a whole block ago, so this does not stall
+        if (nown > 0) {
+          mbar_wait(&o_full[wg], (c - 1) & 1);
           tc_fence_after();
         }
-        if (j == 0) {
-          // first block of a segment: the reference is its exact max (one extra read of S per ~17 blocks)
+        if (nown == 0) {
+          // first own block of a segment: the reference is its exact max (one extra read of S per segment)
           float mx = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int cc = 0; cc < 2; ++cc) {
             uint32_t raw[32];
-            tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+            tmem_ld32(tmem_Sown + cc * 32, raw);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float v = (full || c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
+              const float v = (full || cc * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
               mx = fmaxf(mx, v);
             }
           }
           m = mx;
         }
-        // ONE pass over S in the common case (TMEM reads bound this kernel): probabilities are computed against the
-        // current reference while the block max is tracked; only if some row of the warp outgrew the 2^8 headroom is
-        // O_wg rescaled and the block redone against the new reference (S is still there: s_free not yet signalled).
+        // ONE pass over S in the common case: probabilities are computed against the current reference while the
+        // block max is tracked; only if some row of the warp outgrew the 2^8 headroom is O_wg rescaled and the block
+        // redone against the new reference (S is still there: s_free not yet signalled).
         float rowsum = 0.f;
         for (int attempt = 0;; ++attempt) {
           const float mc = (m == -INFINITY) ? 0.f : m * c2;
           float mx = -INFINITY;
           rowsum = 0.f;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int cc = 0; cc < 2; ++cc) {
             uint32_t raw[32];
-            tmem_ld32(tmem_S + lane_off + wg * 64 + c * 32, raw);
+            tmem_ld32(tmem_Sown + cc * 32, raw);
             tmem_ld_wait();
             if (!full) {  // ragged last block only (warp-uniform): padding columns become -inf -> probability 0
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= kv_valid) raw[i] = 0xff800000u;
+                if (cc * 32 + i >= kv_valid) raw[i] = 0xff800000u;
             }
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) {  // 16-byte units of 8 probabilities
@@ -319,7 +326,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               __align__(16) __half2 h[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
-              const uint32_t unit = static_cast<uint32_t>(c * 4 + uu);
+              const uint32_t unit = static_cast<uint32_t>(cc * 4 + uu);
               const uint32_t off = (unit ^ sw) << 4;
               *reinterpret_cast<uint4*>(tile_hi + off) = *reinterpret_cast<const uint4*>(h);
               if (planes == 2) {
@@ -333,19 +340,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               }
             }
           }
-          if (j == 0 || attempt == 1) break;
+          if (nown == 0 || attempt == 1) break;
           const bool move = mx > m + lazy;  // (m == -inf: any valid score moves it)
           if (!__any_sync(0xffffffffu, move)) break;
           // tcgen05.ld / st are warp-collective: every lane takes part, rows that stay use alpha = 1
           const float alpha = move ? fast_exp2((m - mx) * c2) : 1.f;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int cc = 0; cc < 2; ++cc) {
             uint32_t raw[32];
-            tmem_ld32(tmem_Oown + c * 32, raw);
+            tmem_ld32(tmem_Oown + cc * 32, raw);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-            tmem_st32(tmem_Oown + c * 32, raw);
+            tmem_st32(tmem_Oown + cc * 32, raw);
           }
           tmem_st_wait();
           if (move) {
@@ -354,25 +361,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tc_fence_before();
-        mbar_arrive(&s_free);       // S may be overwritten by the next Q K^T
+        mbar_arrive(&s_free[wg]);   // S_wg may be overwritten by this warpgroup's next Q K^T
         fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
         mbar_arrive(&p_full[wg]);
         l += rowsum;
       }
-      // ---- end of the segment: merge the two halves of every row ----
-      mbar_wait(&o_full[0], (g - 1) & 1);
-      mbar_wait(&o_full[1], (g - 1) & 1);
-      tc_fence_after();
+      // ---- end of the segment: merge the two partial results of every row ----
+      if (nown > 0) {
+        mbar_wait(&o_full[wg], c & 1);  // own last P V (the partner waits for its own before the barrier below)
+        tc_fence_after();
+      }
       if (u + nblk >= u_end) DFU_TR_MARK(8);
-      // (m, l) of the partner thread of the row through the first 8 bytes of the (now idle) P tile rows
+      // (m, l) of the partner thread of the row through the first 8 bytes of the (now idle) P tile rows; l = 0 marks a
+      // warpgroup that had no block in this segment (its accumulator holds stale data and must not be read into the sum)
       *reinterpret_cast<float2*>(tile_hi) = make_float2(m, l);
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // only the two warps that share these 32 rows
       const float2 other = *reinterpret_cast<const float2*>(sP + (wg ^ 1) * kTile + prow);
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both have read before either rewrites its tile
+      tc_fence_after();
       const float m0 = wg == 0 ? m : other.x, m1 = wg == 0 ? other.x : m;
       const float l0 = wg == 0 ? l : other.y, l1 = wg == 0 ? other.y : l;
       const float M = fmaxf(m0, m1);   // finite: every row has at least one valid key in the segment
-      const float w0 = fast_exp2((m0 - M) * c2), w1 = fast_exp2((m1 - M) * c2);  // a half without valid keys: 0
+      const float w0 = l0 > 0.f ? fast_exp2((m0 - M) * c2) : 0.f;
+      const float w1 = l1 > 0.f ? fast_exp2((m1 - M) * c2) : 0.f;
       const float L = l0 * w0 + l1 * w1;
       float acc[32];
       {
@@ -380,11 +391,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tmem_O + lane_off + wg * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(raw[i]) * w0;
+        for (int i = 0; i < 32; ++i) acc[i] = w0 > 0.f ? __uint_as_float(raw[i]) * w0 : 0.f;
         tmem_ld32(tmem_O + 64 + lane_off + wg * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = fmaf(__uint_as_float(raw[i]), w1, acc[i]);
+        for (int i = 0; i < 32; ++i) acc[i] = w1 > 0.f ? fmaf(__uint_as_float(raw[i]), w1, acc[i]) : acc[i];
       }
       tc_fence_before();
       mbar_arrive(&o_free);  // the next segment's first P V may overwrite the accumulators
@@ -417,6 +428,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+      g += nblk;
       u += nblk;
     }
   }
@@ -492,12 +504,13 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(AttnParams p) {
   DFU_TR_END();
 }
 
-static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, int planes, long long plane_stride) {
+static int make_seq_map(CUtensorMap* m, const void* base, int ld, int N, int B, int planes, long long plane_stride,
+                        int box_rows) {
   uint64_t dims[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(N), static_cast<uint64_t>(B),
                       static_cast<uint64_t>(planes)};
   uint64_t str[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(N) * ld * 2,
                      static_cast<uint64_t>(plane_stride) * 2};
-  uint32_t box[4] = {kD, 128, 1, 1};
+  uint32_t box[4] = {kD, static_cast<uint32_t>(box_rows), 1, 1};
   return make_tmap_f16(m, base, 4, dims, str, box);
 }
 
@@ -518,17 +531,17 @@ static int attn_grid(int B, int heads, int Nq, int Nk, int kv_splits) {
   if (kv_splits > 0) {
     G = items * (kv_splits < nblk ? kv_splits : nblk);
   } else {
-    // Measured in the captured UNet step (scripts/trace_step.py): a CTA alone on an SM is latency-bound (~1.9-2.3 us
-    // per 128-key block), two interleaved CTAs take ~2.35 us each, so the goal is two equally loaded CTAs per SM with
-    // at least two blocks each; many-item problems (>= 4 waves) balance by themselves and are not cut.
+    // Measured in the captured UNet step (scripts/trace_step.py): two CTAs per SM interleave better than one, so the
+    // goal is two equally loaded CTAs per SM with at least four 64-key blocks each; many-item problems (>= 4 waves)
+    // balance by themselves and are not cut.
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    if (items >= 4LL * sms || nblk < 8) {
-      // short key sequences (the 577 glyph tokens = 5 blocks): the merge launch (~6-8 us) costs more than the
-      // imbalance it removes (measured: 18.6 us uncut vs 18.5 + 8.0 us cut at 160 tiles x 5 blocks)
+    if (items >= 4LL * sms || Nk < 1024) {
+      // short key sequences (the 577 glyph tokens): the merge launch (~6-8 us) costs more than the imbalance it
+      // removes (measured: 18.6 us uncut vs 18.5 + 8.0 us cut at 160 tiles x 577 keys)
       G = items;
     } else {
       G = 2LL * sms;
-      if (G > total / 2) G = total / 2;
+      if (G > total / 4) G = total / 4;
       if (G < items) G = items;
     }
   }
@@ -555,9 +568,9 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
   DFU_REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "attention: column offsets must be x8");
   CUtensorMap mQ, mK, mV;
   int rc;
-  if ((rc = make_seq_map(&mQ, q, ldq, Nq, B, planes, q_plane_stride))) return rc;
-  if ((rc = make_seq_map(&mK, k, ldk, Nk, B, planes, kv_plane_stride))) return rc;
-  if ((rc = make_seq_map(&mV, v, ldv, Nk, B, planes, kv_plane_stride))) return rc;
+  if ((rc = make_seq_map(&mQ, q, ldq, Nq, B, planes, q_plane_stride, kBQ))) return rc;
+  if ((rc = make_seq_map(&mK, k, ldk, Nk, B, planes, kv_plane_stride, kBKV))) return rc;
+  if ((rc = make_seq_map(&mV, v, ldv, Nk, B, planes, kv_plane_stride, kBKV))) return rc;
   AttnParams p;
   p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk; p.planes = planes;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -583,7 +596,7 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
     p.ws_o = static_cast<float*>(workspace);
     p.ws_ml = p.ws_o + slots * 128 * 64;
   }
-  const size_t smem = static_cast<size_t>(planes) * kTile * (1 + 2 + 2 + 2) + 192;
+  const size_t smem = static_cast<size_t>(planes) * (kTile * 3 + 2 * kRing * kKvTile) + 256;
   static bool attr = false;
   if (!attr) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -68,10 +68,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// same with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires,
-// instead of returning after ~50 cycles.  ncu showed 16 epilogue warps per SM spinning ~95 times each on the
-// accumulator barrier during the main loop (391k try_wait + clock reads per launch), taking issue slots from the
-// single-thread TMA producer and MMA issuer.
+// Bounded wait: a protocol bug traps (process dies with an error) instead of hanging the GPU box.
+// The slow path backs off with nanosleep between probes and counts iterations instead of reading the clock: ncu showed
+// the plain probe loop (try_wait returns after ~50 cycles; + clock read, compare, branch) taking 40% of ALL issued
+// instructions of the attention kernel — issue slots stolen from the warps doing the exponentials.
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned spins = 0;
+  for (;;) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if (++spins > (1u << 26)) {  // >= 2 s
+      printf("dfu: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_ns(bar, parity, 32); }
+// same with a suspend-time hint (ns) on the probe itself
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
@@ -83,31 +97,8 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
-// Long waits (epilogue warps waiting for the whole main loop): hardware sleep, bounded like mbar_wait.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("dfu: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-// Bounded wait: a protocol bug traps (process dies with an error) instead of hanging the GPU box.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns);
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  // the hinted form parks the thread in hardware until the phase flips (ncu: the plain form returned after ~50 cycles
-  // and the spin loops — try_wait, clock read, compare, branch — were 20% of all instructions of the attention kernel)
-  while (!mbar_try_wait_hint(bar, parity, 10000u)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("dfu: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
+// Long waits (epilogue warps waiting for the whole main loop): coarser back-off
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait_ns(bar, parity, 200); }
 
 // ----------------------------------------------------------------------------------------------
 // programmatic dependent launch: every kernel lets its successor start launching at once (its CTAs only fill
