@@ -197,65 +197,89 @@ struct SmallOut {
   const float* coef;   // device [2] = {cx, ce}
 };
 
-__global__ void __launch_bounds__(256) conv_small_out_kernel(SmallOut p) {
+__global__ void __launch_bounds__(256, 2) conv_small_out_kernel(SmallOut p, int w_in_smem) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_CONV_OUT);
+  // The packed weights ([Cout][k*k][Cin], up to ~150 KB) are constants: each CTA copies them to shared memory ONCE,
+  // before waiting for the producer of the input, and its eight warps then walk pixels with a grid stride (was: one
+  // warp per pixel re-reading all weights through L1 — 592 us for the 128->3 decoder output conv at 512x512).
+  extern __shared__ __align__(16) float sw[];
+  const int kk = p.ksz * p.ksz;
+  const int wq = p.Cout * kk * (p.Cin >> 2);  // float4 count
+  if (w_in_smem) {
+    for (int i = threadIdx.x; i < wq; i += blockDim.x)
+      reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+    __syncthreads();
+  }
+  const float* wbase = w_in_smem ? sw : p.w;
   pdl_wait();
   DFU_TR_MARK(6);
   const int lane = threadIdx.x & 31;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long npix = static_cast<long long>(p.B) * p.H * p.W;
-  if (warp >= npix) return;
-  const int x = static_cast<int>(warp % p.W);
-  const int y = static_cast<int>((warp / p.W) % p.H);
-  const int b = static_cast<int>(warp / (static_cast<long long>(p.W) * p.H));
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int pad = p.ksz / 2;
-  const int kk = p.ksz * p.ksz;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const int C4 = p.Cin >> 2;
-  for (int t = 0; t < kk; ++t) {
-    const int iy = y + t / p.ksz - pad, ix = x + t % p.ksz - pad;
-    if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
-    const float4* xr = reinterpret_cast<const float4*>(p.x + ((static_cast<size_t>(b) * p.H + iy) * p.W + ix) * p.Cin);
-    for (int q = lane; q < C4; q += 32) {
-      const float4 xv = xr[q];
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += nwarps) {
+    const int x = static_cast<int>(pix % p.W);
+    const int y = static_cast<int>((pix / p.W) % p.H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(p.W) * p.H));
+    float acc[8];
 #pragma unroll
-      for (int co = 0; co < 8; ++co) {
-        if (co < p.Cout) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(co) * kk + t) * p.Cin) + q);
-          acc[co] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // all taps of a channel quad are requested before the first FMA: one memory latency per quad, not one per tap
+    const float* xrow[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = y + t / p.ksz - pad, ix = x + t % p.ksz - pad;
+      const bool ok = t < kk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      xrow[t] = ok ? p.x + ((static_cast<size_t>(b) * p.H + iy) * p.W + ix) * p.Cin : nullptr;
+    }
+    for (int q = lane; q < C4; q += 32) {
+      float4 xv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        xv[t] = xrow[t] ? reinterpret_cast<const float4*>(xrow[t])[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t < kk) {
+#pragma unroll
+          for (int co = 0; co < 8; ++co) {
+            if (co < p.Cout) {
+              const float4 wv = *(reinterpret_cast<const float4*>(wbase + (static_cast<size_t>(co) * kk + t) * p.Cin) + q);
+              acc[co] += wv.x * xv[t].x + wv.y * xv[t].y + wv.z * xv[t].z + wv.w * xv[t].w;
+            }
+          }
         }
       }
     }
-  }
 #pragma unroll
-  for (int co = 0; co < 8; ++co) acc[co] = warp_sum(acc[co]);
-  if (lane == 0) {
-    float v[8];
+    for (int co = 0; co < 8; ++co) acc[co] = warp_sum(acc[co]);
+    if (lane == 0) {
+      float v[8];
 #pragma unroll
-    for (int co = 0; co < 8; ++co) v[co] = (co < p.Cout) ? acc[co] + (p.bias ? p.bias[co] : 0.f) : 0.f;
-    int nout = p.Cout;
-    float o[8];
-    if (p.w2) {
-      nout = p.Cout2;
-      for (int j = 0; j < p.Cout2; ++j) {
-        float a = p.b2 ? p.b2[j] : 0.f;
-        for (int co = 0; co < p.Cout; ++co) a += p.w2[j * p.Cout + co] * v[co];
-        o[j] = a;
+      for (int co = 0; co < 8; ++co) v[co] = (co < p.Cout) ? acc[co] + (p.bias ? p.bias[co] : 0.f) : 0.f;
+      int nout = p.Cout;
+      float o[8];
+      if (p.w2) {
+        nout = p.Cout2;
+        for (int j = 0; j < p.Cout2; ++j) {
+          float a = p.b2 ? p.b2[j] : 0.f;
+          for (int co = 0; co < p.Cout; ++co) a += p.w2[j * p.Cout + co] * v[co];
+          o[j] = a;
+        }
+      } else {
+#pragma unroll
+        for (int co = 0; co < 8; ++co) o[co] = v[co];
       }
-    } else {
-#pragma unroll
-      for (int co = 0; co < 8; ++co) o[co] = v[co];
-    }
-    const size_t hw = static_cast<size_t>(p.H) * p.W;
-    const size_t base = static_cast<size_t>(b) * nout * hw + static_cast<size_t>(y) * p.W + x;
-    for (int j = 0; j < nout; ++j) {
-      if (p.out) p.out[base + j * hw] = o[j];
-      if (p.prev) p.prev[base + j * hw] = p.coef[0] * p.sample[base + j * hw] + p.coef[1] * o[j];
+      const size_t hw = static_cast<size_t>(p.H) * p.W;
+      const size_t base = static_cast<size_t>(b) * nout * hw + static_cast<size_t>(y) * p.W + x;
+      for (int j = 0; j < nout; ++j) {
+        if (p.out) p.out[base + j * hw] = o[j];
+        if (p.prev) p.prev[base + j * hw] = p.coef[0] * p.sample[base + j * hw] + p.coef[1] * o[j];
+      }
     }
   }
+  DFU_TR_END();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -476,8 +500,19 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   p.w = w; p.bias = bias; p.w2 = w2; p.b2 = b2; p.Cout2 = Cout2; p.out = out;
   p.sample = sample; p.prev = prev; p.coef = coef;
   const long long npix = static_cast<long long>(B) * H * W;
-  const long long blocks = (npix * 32 + 255) / 256;
-  DFU_CHECK_CUDA(launch_k(conv_small_out_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  const size_t wbytes = static_cast<size_t>(Cout) * ksz * ksz * Cin * sizeof(float);
+  const int w_in_smem = wbytes <= 200 * 1024;
+  static bool attr = false;
+  if (!attr) {
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_small_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  // eight pixels per CTA pass; enough CTAs for every SM, few enough that the weight copy is amortised over many pixels
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const long long per_sm = wbytes > 100 * 1024 ? 1 : 2;
+  long long blocks = (npix + 7) / 8;
+  if (blocks > sms * per_sm) blocks = sms * per_sm;
+  DFU_CHECK_CUDA(launch_k(conv_small_out_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), w_in_smem ? wbytes : 0, static_cast<cudaStream_t>(stream), p, w_in_smem));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -38,16 +38,19 @@ class DiffUTEPipeline:
         self._rows_cache = {}
 
     @classmethod
-    def from_pretrained(cls, path, unet_precision="fp16", vae_precision="fp16x2", scheduler_cls=DDIMScheduler, **kw):
+    def from_pretrained(cls, path, unet_precision="fp16", vae_precision="fp16x2", scheduler_cls=DDIMScheduler,
+                        vae_encoder_precision=None, **kw):
         """Folder layout of the reference: <path>/{unet,vae,scheduler}/ (app.ipynb:545-553)."""
         from .unet import UNet2DConditionModel
         from .vae import AutoencoderKL
         unet = UNet2DConditionModel.from_pretrained(path, "unet", precision=unet_precision)
-        vae = AutoencoderKL.from_pretrained(path, "vae", precision=vae_precision)
+        vae = AutoencoderKL.from_pretrained(path, "vae", precision=vae_precision,
+                                            encoder_precision=vae_encoder_precision)
         return cls(vae, unet, scheduler_cls.from_pretrained(path, "scheduler"), **kw)
 
     @classmethod
-    def from_synthetic(cls, unet_precision="fp16", vae_precision="fp16x2", seed: int = 1234, state_dicts=None):
+    def from_synthetic(cls, unet_precision="fp16", vae_precision="fp16x2", seed: int = 1234, state_dicts=None,
+                       vae_encoder_precision=None):
         from . import arch, synthetic
         from .unet import UNet2DConditionModel
         from .vae import AutoencoderKL
@@ -55,7 +58,7 @@ class DiffUTEPipeline:
             state_dicts = (synthetic.make_state_dict(arch.unet_param_shapes(), seed),
                            synthetic.make_state_dict(arch.vae_param_shapes(), seed))
         unet = UNet2DConditionModel(state_dicts[0], precision=unet_precision)
-        vae = AutoencoderKL(state_dicts[1], precision=vae_precision)
+        vae = AutoencoderKL(state_dicts[1], precision=vae_precision, encoder_precision=vae_encoder_precision)
         return cls(vae, unet, DDIMScheduler())
 
     # ------------------------------------------------------------------------------------------

@@ -23,7 +23,8 @@ t_cpu = time.time() - t0
 res = {"px": px, "steps": steps, "cpu_oracle_seconds": t_cpu, "cpu_threads": torch.get_num_threads(), "modes": {}}
 for m in modes:
     up, vp = {"mixed": ("fp16", "fp16x2"), "fp16x2": ("fp16x2", "fp16x2"), "fp16": ("fp16", "fp16")}[m]
-    pipe = DiffUTEPipeline.from_synthetic(up, vp, state_dicts=(usd, vsd))
+    pipe = DiffUTEPipeline.from_synthetic(up, vp, state_dicts=(usd, vsd),
+                                          vae_encoder_precision="fp16" if m == "mixed" else None)
     out = pipe(masked_image=inp["masked_image"], mask_image=inp["mask"], glyph_embeds=inp["glyph_embeds"],
                latents=inp["latents"], posterior_noise=inp["posterior_noise"], num_inference_steps=steps).images.cpu()
     err = ((out - ref).abs().max() / ref.abs().max()).item()
