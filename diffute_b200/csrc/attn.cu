@@ -301,11 +301,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float mc = (m == -INFINITY) ? 0.f : m * c2;
           float mx = -INFINITY;
           rowsum = 0.f;
+          // both 32-column halves are requested before the first is consumed: one TMEM latency per block, not two
+          uint32_t raw2[2][32];
+          tmem_ld32(tmem_Sown, raw2[0]);
+          tmem_ld32(tmem_Sown + 32, raw2[1]);
+          tmem_ld_wait();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
-            uint32_t raw[32];
-            tmem_ld32(tmem_Sown + cc * 32, raw);
-            tmem_ld_wait();
+            uint32_t(&raw)[32] = raw2[cc];
             if (!full) {  // ragged last block only (warp-uniform): padding columns become -inf -> probability 0
 #pragma unroll
               for (int i = 0; i < 32; ++i)

@@ -12,7 +12,7 @@ from diffute_b200.pipeline import DiffUTEPipeline
 mode = sys.argv[1] if len(sys.argv) > 1 else "mixed"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 up, vp = {"mixed": ("fp16", "fp16x2"), "fp16x2": ("fp16x2", "fp16x2"), "fp16": ("fp16", "fp16")}[mode]
-pipe = DiffUTEPipeline.from_synthetic(up, vp)
+pipe = DiffUTEPipeline.from_synthetic(up, vp, vae_encoder_precision="fp16" if mode == "mixed" else None)
 inp = synthetic.make_inputs(B, 512, 512)
 dev = pipe.device
 h = w = 64
