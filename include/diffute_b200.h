@@ -184,9 +184,11 @@ int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int ld_in,
  * reached from app.ipynb:814.  Q/K/V are fp16 operand matrices [planes][B*N][ld] with head h at columns
  * col0 + 64*h (so a fused QKV projection output can be passed three times with different col0).  The result is
  * written as an fp16 operand [planes][B*Nq][ldo] for the to_out projection.
- * kv_splits: 0 = automatic.  When the (query tile, head, sample) grid cannot keep two CTAs on every SM the key range is
- * cut into kv_splits slices (flash-decoding style); partial (O, max, sum) go to `workspace`
- * (dfu_attention_workspace bytes) and a merge kernel combines them in slice order (deterministic).
+ * Work distribution: the (sample, head, 128-query tile) items x 64-key blocks sequence is cut into equal contiguous
+ * ranges, one per CTA ("stream-K"); kv_splits = 0 chooses the number of ranges automatically (2 x SMs for long key
+ * sequences, one item per CTA for short ones), kv_splits = k > 0 forces items x k ranges (1 = never cut an item).  Items
+ * cut across CTAs leave partial (O, max, sum) in `workspace` (dfu_attention_workspace bytes) and a merge kernel combines
+ * the pieces in key order (deterministic, bit-identical run to run).
  */
 size_t dfu_attention_workspace(int B, int heads, int Nq, int Nk, int kv_splits);
 int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, const void* k, int ldk, int k_col0,
