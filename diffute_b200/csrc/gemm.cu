@@ -266,7 +266,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * 128u;
+  // FP16X2 (npass = 3): a stage holds the hi AND lo tiles of both operands, fetched once, and the three products
+  // hi*hi + lo*hi + hi*lo are issued from it — 4 tile loads per k-block instead of 6 (these contractions are bound by
+  // L2 -> shared-memory traffic: arithmetic intensity x1.5)
+  const uint32_t nplane = p.npass == 3 ? 2u : 1u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  const uint32_t stage_bytes = nplane * (kABytes + b_bytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -326,8 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====================================================================
     if (lane == 0) {
-      const int kbg0 = p.g[0].kb_per_pass * p.npass;
-      // k-block -> (group, pass, tap, channel chunk) and the two loads of that k-block
+      const int kbg0 = p.g[0].kb_per_pass;
+      // k-block -> (group, tap, channel chunk) and the loads of that k-block (hi [+ lo] tile of each operand)
       auto issue = [&](int kb, int stage, bool load_a, bool load_b) {
         int r = kb, gi = 0;
         if (r >= kbg0) {
@@ -335,26 +340,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           gi = 1;
         }
         const GroupDev& G = p.g[gi];
-        const int pass = r / G.kb_per_pass;
-        r -= pass * G.kb_per_pass;
         const int tap = r / G.nchunks;
         const int chunk = r - tap * G.nchunks;
-        const int a_sel = (pass == 1) ? G.a_plane : 0;
-        const int b_sel = (pass == 2) ? G.b_plane : 0;
         const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
         const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
         uint8_t* sA = smem + stage * stage_bytes;
-        uint8_t* sB = sA + kABytes;
-        if (load_b) {  // the k-block's first load also arms the barrier with the bytes of BOTH operands
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes[gi] + p.b_tx_bytes);
-          tma_load_2d(sB, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, n_tile0 + b_sel);
+        uint8_t* sB = sA + nplane * kABytes;
+        if (load_b) {  // the k-block's first load also arms the barrier with the bytes of ALL its tiles
+          mbar_arrive_expect_tx(&full_bar[stage], nplane * (p.a_tx_bytes[gi] + p.b_tx_bytes));
+          for (uint32_t pl = 0; pl < nplane; ++pl)
+            tma_load_2d(sB + pl * b_bytes, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK,
+                        n_tile0 + static_cast<int>(pl) * G.b_plane);
         }
         if (load_a) {
-          if (G.a_mode == 0) {
-            tma_load_2d(sA, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
-          } else {
-            tma_load_4d(sA, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
-                        img0 + G.dn[tap] + a_sel);
+          for (uint32_t pl = 0; pl < nplane; ++pl) {
+            const int a_sel = static_cast<int>(pl) * G.a_plane;
+            if (G.a_mode == 0) {
+              tma_load_2d(sA + pl * kABytes, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
+            } else {
+              tma_load_4d(sA + pl * kABytes, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
+                          img0 + G.dn[tap] + a_sel);
+            }
           }
         }
       };
@@ -392,14 +398,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         if (kb == kb0) DFU_TR_SHARED_MARK(7);
         const uint32_t sA = smem_u32(smem + stage * stage_bytes);
-        const uint32_t sB = sA + kABytes;
-        const uint64_t adesc = umma_desc_sw128(sA);
-        const uint64_t bdesc = umma_desc_sw128(sB);
+        const uint32_t sB = sA + nplane * kABytes;
+        const int nprod = p.npass == 3 ? 3 : 1;
+        for (int ps = 0; ps < nprod; ++ps) {  // hi*hi [, lo*hi, hi*lo] from the same stage
+          const uint64_t adesc = umma_desc_sw128(sA + (ps == 1 ? kABytes : 0u));
+          const uint64_t bdesc = umma_desc_sw128(sB + (ps == 2 ? b_bytes : 0u));
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-          umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+            umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > kb0 || ps > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees this smem slot when the MMAs above have read it
         if (++stage == p.stages) {
@@ -646,7 +655,7 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
     DFU_REQUIRE(o.a_mode == 0 || (o.a_mode == 1 && d->conv), "gemm: image operand needs conv=1");
     DFU_REQUIRE(!(o.a_mode == 0 && o.ntaps != 1), "gemm: matrix operand must have ntaps=1");
     DFU_REQUIRE(!(o.a_mode == 1 && o.a_c != o.k_per_tap), "gemm: a_c must equal k_per_tap");
-    total_kb += o.ntaps * (o.k_per_tap / kBlockK) * d->npass;
+    total_kb += o.ntaps * (o.k_per_tap / kBlockK);  // npass = 3 shares the k-block's tiles among its three products
   }
   pl->total_kb = total_kb;
   if (d->conv) {
@@ -695,7 +704,7 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
         if (sp > 1 && total_kb / sp < 2) continue;
         const int ctas = tiles * sp;
         const int kb = (total_kb + sp - 1) / sp;
-        const double cta = 2500.0 + kb * 4.0 * per_k16 + (c / 32) * 450.0;  // prologue/fill + main loop + epilogue
+        const double cta = 2500.0 + kb * 4.0 * per_k16 * d->npass + (c / 32) * 450.0;  // prologue/fill + main loop + epilogue
         const double rounds = static_cast<double>((ctas + sms - 1) / sms);
         double t = rounds * cta;
         if (sp > 1) {
@@ -717,11 +726,12 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
   DFU_REQUIRE(d->epi != DFU_EPI_GEGLU || bn_ % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0, got %d", bn_);
   pl->block_n = bn_;
   pl->tiles_n = d->n / bn_;
-  DFU_REQUIRE(splits >= 1 && splits <= total_kb, "gemm: bad splits=%d (k-blocks %d)", splits, total_kb);
+  DFU_REQUIRE(splits >= 1, "gemm: bad splits=%d", splits);
+  if (splits > total_kb) splits = total_kb;  // (tables tuned when a 3-pass K loop was three times as long)
   pl->splits = splits;
   pl->ws_bytes = splits > 1 ? static_cast<size_t>(splits) * d->m * d->n * sizeof(float) : 0;
   int stages = d->stages;
-  const size_t stage_bytes = kABytes + static_cast<size_t>(bn_) * 128;
+  const size_t stage_bytes = (d->npass == 3 ? 2 : 1) * (kABytes + static_cast<size_t>(bn_) * 128);
   if (stages <= 0) {
     // ~1.4 us of TMA latency (measured, scripts/trace_step.py) at >= 64 B/clk per SM wants ~100 KiB in flight; stay
     // under half the SM so that the NEXT kernel's CTA can be co-resident and prefetch its weights (PDL)

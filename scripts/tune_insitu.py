@@ -4,7 +4,8 @@ in-kernel timeline records of the diagnostic library (diffute_b200/trace.py).  T
 to the step's critical path: (its last CTA's exit [+ the split-K reduce launch that follows]) - (previous kernel's
 last exit).  Round r gives every shape its r-th candidate; a second phase re-times the best few per shape with all
 other shapes at their winners.
-  DFU_TRACE=1 python scripts/tune_insitu.py [batch] [px]  ->  gpurun_out/tuning_b200.json (+ tune_insitu_log.json)"""
+  DFU_TRACE=1 python scripts/tune_insitu.py [batch] [px] [unet|vae]  ->  gpurun_out/tuning_b200.json (+ log)
+`vae` tunes the shapes of one VAE encode + decode (captured as a graph the same way) instead of the UNet step."""
 import ctypes as C, json, os, sys, time
 os.environ["DFU_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,8 +15,9 @@ from diffute_b200.pipeline import DiffUTEPipeline
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 px = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+WHAT = sys.argv[3] if len(sys.argv) > 3 else "unet"
 MAXR = int(os.environ.get("TUNE_ROUNDS", "120"))
-pipe = DiffUTEPipeline.from_synthetic("fp16", "fp16x2")
+pipe = DiffUTEPipeline.from_synthetic("fp16", "fp16x2", vae_encoder_precision="fp16")
 inp = synthetic.make_inputs(B, px, px)
 dev = pipe.device
 h = w = px // 8
@@ -47,7 +49,15 @@ def launch_gemm(d, ws=None):
 ops.launch_gemm = launch_gemm
 
 
+x_img = inp["masked_image"].to(dev)
+lat_in = inp["latents"].to(dev)
+pipe.vae.ws.ensure(512 << 20)
+
+
 def step():
+    if WHAT == "vae":
+        pipe.vae.encode(x_img)
+        return pipe.vae.decode(lat_in, pre_scale=1 / 0.18215)
     return pipe.unet._forward_impl(B, h, w, srcs=[lat, mask, ml], t=state[:B], tproj=tproj)
 
 
@@ -134,7 +144,7 @@ def measure(nrep=2):
 for _ in range(2):
     step()
 torch.cuda.synchronize()
-trace.enable(1 << 18)
+trace.enable(1 << 20 if WHAT == "vae" else 1 << 18)
 base_order, base_costs, base_span = measure()
 print(f"baseline span {base_span:.1f} us, {len(base_order)} gemm launches, {len(SHAPES)} shapes", flush=True)
 base_table = dict(ops.TUNE_TABLE)
@@ -207,9 +217,9 @@ print(f"tuned span {span:.1f} us (baseline {base_span:.1f}); gemm critical-path 
 os.makedirs("gpurun_out", exist_ok=True)
 merged = {k: list(v) for k, v in base_table.items()}
 merged.update(table)
-with open("gpurun_out/tuning_b200.json", "w") as f:
+with open("gpurun_out/tuning_b200.json" if WHAT == "unet" else "gpurun_out/tuning_b200_vae.json", "w") as f:
     json.dump({"meta": {"device": torch.cuda.get_device_name(0), "batch": B, "px": px, "method": "in-situ graph replay, in-kernel timestamps (scripts/tune_insitu.py)",
                         "key": "conv:m:n:k_blocks(64, all passes):epilogue", "value": "[block_n, splits, stages]",
                         "span_us": span, "baseline_span_us": base_span}, "table": merged}, f, indent=0)
-with open("gpurun_out/tune_insitu_log.json", "w") as f:
+with open(f"gpurun_out/tune_insitu_log_{WHAT}.json", "w") as f:
     json.dump({k: {str(cfg): v for cfg, v in RESULT[k].items()} for k in RESULT}, f)
