@@ -118,18 +118,19 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
   const float b0 = (bias && co < Cout) ? __ldg(bias + co) : 0.f;
   pdl_wait();
   DFU_TR_MARK(6);
-  const long long pix0 = static_cast<long long>(blockIdx.x) * kSmallInPix;
-  const long long npix = static_cast<long long>(B) * H * W;
+  const int pix0 = blockIdx.x * kSmallInPix;  // pixel indices fit 32 bits (checked by the host): no 64-bit divisions
+  const int npix = B * H * W;
   for (int i = threadIdx.x; i < kSmallInPix * K; i += blockDim.x) {
     const int k = i / kSmallInPix, pl = i % kSmallInPix;  // consecutive threads -> consecutive pixels (coalesced NCHW)
-    const long long pix = pix0 + pl;
+    const int pix = pix0 + pl;
     float v = 0.f;
     if (pix < npix) {
       const int c = k / kk, t = k % kk;
       const int ky = t / ksz, kx = t % ksz;
-      const int x = static_cast<int>(pix % W);
-      const int y = static_cast<int>((pix / W) % H);
-      const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+      const int x = pix % W;
+      const int yb = pix / W;
+      const int y = yb % H;
+      const int b = yb / H;
       const int iy = y + ky - pad, ix = x + kx - pad;
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
         int cc = c, si = 0;
@@ -171,7 +172,7 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
     }
 #pragma unroll
     for (int j = 0; j < kSmallInPix; ++j)
-      if (pix0 + j < npix) out[(pix0 + j) * Cout + co] = acc[j];
+      if (pix0 + j < npix) out[static_cast<size_t>(pix0 + j) * Cout + co] = acc[j];
   }
   DFU_TR_END();
 }
@@ -197,7 +198,8 @@ struct SmallOut {
   const float* coef;   // device [2] = {cx, ce}
 };
 
-__global__ void __launch_bounds__(256, 2) conv_small_out_kernel(SmallOut p, int w_in_smem) {
+template <bool kSmemW>
+__global__ void __launch_bounds__(256, 2) conv_small_out_kernel(SmallOut p) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_CONV_OUT);
   // The packed weights ([Cout][k*k][Cin], up to ~150 KB) are constants: each CTA copies them to shared memory ONCE,
@@ -206,23 +208,26 @@ __global__ void __launch_bounds__(256, 2) conv_small_out_kernel(SmallOut p, int 
   extern __shared__ __align__(16) float sw[];
   const int kk = p.ksz * p.ksz;
   const int wq = p.Cout * kk * (p.Cin >> 2);  // float4 count
-  if (w_in_smem) {
+  if (kSmemW) {
     for (int i = threadIdx.x; i < wq; i += blockDim.x)
       reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
     __syncthreads();
   }
-  const float* wbase = w_in_smem ? sw : p.w;
+  // (compile-time choice: a run-time select between the shared and the global pointer made every weight read a
+  // generic-address load with 64-bit arithmetic — with the 64-bit pixel divisions, 2083 instructions per pixel, ncu)
+  const float* wbase = kSmemW ? sw : p.w;
   pdl_wait();
   DFU_TR_MARK(6);
   const int lane = threadIdx.x & 31;
-  const long long npix = static_cast<long long>(p.B) * p.H * p.W;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int npix = p.B * p.H * p.W;  // < 2^31 (checked by the host): 32-bit index arithmetic
+  const int nwarps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
   const int pad = p.ksz / 2;
   const int C4 = p.Cin >> 2;
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += nwarps) {
-    const int x = static_cast<int>(pix % p.W);
-    const int y = static_cast<int>((pix / p.W) % p.H);
-    const int b = static_cast<int>(pix / (static_cast<long long>(p.W) * p.H));
+  for (int pix = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5); pix < npix; pix += nwarps) {
+    const int x = pix % p.W;
+    const int yb = pix / p.W;
+    const int y = yb % p.H;
+    const int b = yb / p.H;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -478,6 +483,7 @@ int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* 
   s.bstride[0] = bstride0; s.bstride[1] = bstride1; s.bstride[2] = bstride2;
   s.nhwc = nhwc;
   const long long npix = static_cast<long long>(B) * H * W;
+  DFU_REQUIRE(npix < (1LL << 31), "conv_small_in: %lld pixels exceed the 32-bit index range", npix);
   const int blocks = static_cast<int>((npix + kSmallInPix - 1) / kSmallInPix);
   const size_t smem = static_cast<size_t>(kSmallInPix) * Cin * ksz * ksz * sizeof(float);
   DFU_REQUIRE(Cout >= 1 && Cout <= 512, "conv_small_in: Cout=%d (one thread per output channel, max 512)", Cout);
@@ -501,18 +507,24 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   p.sample = sample; p.prev = prev; p.coef = coef;
   const long long npix = static_cast<long long>(B) * H * W;
   const size_t wbytes = static_cast<size_t>(Cout) * ksz * ksz * Cin * sizeof(float);
-  const int w_in_smem = wbytes <= 200 * 1024;
+  // staging the weights pays only when a CTA then walks many pixels (VAE maps); the 64x64 UNet output conv keeps
+  // one warp per pixel reading the weights through L1 (measured 11 us vs 19 us with the 46 KB copy per CTA)
+  const int w_in_smem = wbytes <= 200 * 1024 && npix >= 64LL * 8 * (num_sms() > 0 ? num_sms() : 148);
   static bool attr = false;
   if (!attr) {
-    DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_small_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_small_out_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   // eight pixels per CTA pass; enough CTAs for every SM, few enough that the weight copy is amortised over many pixels
   const int sms = num_sms() > 0 ? num_sms() : 148;
   const long long per_sm = wbytes > 100 * 1024 ? 1 : 2;
   long long blocks = (npix + 7) / 8;
-  if (blocks > sms * per_sm) blocks = sms * per_sm;
-  DFU_CHECK_CUDA(launch_k(conv_small_out_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), w_in_smem ? wbytes : 0, static_cast<cudaStream_t>(stream), p, w_in_smem));
+  if (w_in_smem && blocks > sms * per_sm) blocks = sms * per_sm;
+  DFU_REQUIRE(npix < (1LL << 31), "conv_small_out: %lld pixels exceed the 32-bit index range", npix);
+  if (w_in_smem)
+    DFU_CHECK_CUDA(launch_k(conv_small_out_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), wbytes, static_cast<cudaStream_t>(stream), p));
+  else
+    DFU_CHECK_CUDA(launch_k(conv_small_out_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
