@@ -27,6 +27,7 @@ def _rand(shape, seed, scale=1.0):
     (2, 5, 4096, 577, False),     # cross-attention over the glyph tokens (ragged key tail)
     (1, 20, 64, 577, False),
     (1, 2, 200, 130, False),      # ragged both ways
+    (1, 2, 64, 4096, False),      # two work items, 64 key blocks each: cut into six pieces per item + merge
 ])
 def test_attention(ops, planes, B, heads, Nq, Nk, fused):
     C = heads * 64

@@ -160,3 +160,15 @@ def test_elementwise_and_softmax(ops):
         t = torch.zeros((planes, 1000, 300), dtype=torch.float16, device="cuda")
         ops.transpose_f16(p16, t)
         assert torch.equal(t, p16.transpose(1, 2))
+
+
+def test_groupnorm_two_launch_path_subprocess():
+    """The statistics + apply pair (used for maps too large for the cluster kernel, e.g. VAE 512x512) on the standard
+    shapes: DFU_GN_CLUSTER=0 is read once per process, so the same test runs again in a child process."""
+    import os, subprocess, sys
+    if os.environ.get("DFU_GN_CLUSTER") == "0":
+        pytest.skip("already the child")
+    env = dict(os.environ, DFU_GN_CLUSTER="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "test_groupnorm and not subprocess"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
