@@ -65,7 +65,7 @@ __host__ __device__ __forceinline__ int attn_cta_of(const AttnParams& p, long lo
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // not volatile: a pure function the scheduler may reorder
   return y;
 }
 
@@ -163,18 +163,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         int item, jb0, n, b, head, q0;
         seg_of(u, item, jb0, n);
         coords(item, b, head, q0);
-        if (seg > 0) mbar_wait(&q_free, (seg - 1) & 1);  // previous segment's Q K^T MMAs have all read Q
+        if (seg > 0) mbar_wait_ns(&q_free, (seg - 1) & 1, 64, 512);  // previous segment's Q K^T MMAs have all read Q
         mbar_arrive_expect_tx(&q_full, planes * kTile);
         for (int pl = 0; pl < planes; ++pl)
           tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
         for (int j = 0; j < n; ++j, ++g) {
           const int slot = g % kRing;
           const uint32_t par = ((g / kRing) & 1) ^ 1u;
-          mbar_wait(&k_empty[slot], par);
+          mbar_wait_ns(&k_empty[slot], par, 64, 512);  // (a polling warp takes issue slots from the softmax warps)
           mbar_arrive_expect_tx(&k_full[slot], planes * kKvTile);
           for (int pl = 0; pl < planes; ++pl)
             tma_load_4d(sK + (slot * planes + pl) * kKvTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
-          mbar_wait(&v_empty[slot], par);
+          mbar_wait_ns(&v_empty[slot], par, 64, 512);
           mbar_arrive_expect_tx(&v_full[slot], planes * kKvTile);
           for (int pl = 0; pl < planes; ++pl)
             tma_load_4d(sV + (slot * planes + pl) * kKvTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
@@ -218,9 +218,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (n > 1) issue_qk(g + 1, n == 2);
         for (int j = 0; j < n; ++j) {
           const int gg = g + j, slot = gg % kRing, h = gg & 1, c = gg >> 1;
+          mbar_wait(&p_full[h], c & 1);  // softmax of block gg done (its s_free arrived at the same time)
+          // the warpgroup's NEXT S first — it is waiting for it — then the P V of the block it just finished, whose
+          // result is only needed one block later
+          if (j + 2 < n) issue_qk(gg + 2, j + 3 == n);
           mbar_wait(&v_full[slot], (gg / kRing) & 1);
           if (j == 0 && seg > 0) mbar_wait(&o_free, (seg - 1) & 1);  // the previous item's accumulators were read
-          mbar_wait(&p_full[h], c & 1);
           tc_fence_after();
           uint32_t acc = j >= 2 ? 1u : 0u;  // O_h accumulates in TMEM over the warpgroup's blocks of a segment
           for (int ps = 0; ps < npass; ++ps) {
@@ -237,7 +240,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           umma_commit(&o_full[h]);
           umma_commit(&v_empty[slot]);
-          if (j + 2 < n) issue_qk(gg + 2, j + 3 == n);
         }
         g += n;
         u += n;
@@ -249,7 +251,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = threadIdx.x & 127;   // query row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c2 = p.scale_log2;
-    const float lazy = 8.0f / c2;      // the reference max moves only when exceeded by 2^8 in the exp2 domain
     const uint32_t pair_bar = 1u + static_cast<uint32_t>(warp & 3);  // named barrier of warps (w, w + 4)
     const uint32_t prow = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
@@ -299,16 +300,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float rowsum = 0.f;
         for (int attempt = 0;; ++attempt) {
           const float mc = (m == -INFINITY) ? 0.f : m * c2;
-          float mx = -INFINITY;
+          float big = 0.f;  // largest 8-element partial sum: > 2^11 means some probability outgrew the headroom
           rowsum = 0.f;
-          // both 32-column halves are requested before the first is consumed: one TMEM latency per block, not two
-          uint32_t raw2[2][32];
-          tmem_ld32(tmem_Sown, raw2[0]);
-          tmem_ld32(tmem_Sown + 32, raw2[1]);
-          tmem_ld_wait();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
-            uint32_t(&raw)[32] = raw2[cc];
+            uint32_t raw[32];  // (both halves in flight at once was measured: no gain, and it spills at 96 registers)
+            tmem_ld32(tmem_Sown + cc * 32, raw);
+            tmem_ld_wait();
             if (!full) {  // ragged last block only (warp-uniform): padding columns become -inf -> probability 0
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -318,14 +316,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int uu = 0; uu < 4; ++uu) {  // 16-byte units of 8 probabilities
               float pv[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pv[i] = __uint_as_float(raw[uu * 8 + i]);
-              // short dependency chains: a tree per unit, one add / max per unit into the running values
-              const float um = fmaxf(fmaxf(fmaxf(pv[0], pv[1]), fmaxf(pv[2], pv[3])),
-                                     fmaxf(fmaxf(pv[4], pv[5]), fmaxf(pv[6], pv[7])));
-              mx = fmaxf(mx, um);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(pv[i] * c2 - mc);
-              rowsum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+              for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(__uint_as_float(raw[uu * 8 + i]) * c2 - mc);
+              // the kernel is bound by instruction issue (a single spinning warp costs 12%): no per-element max — the
+              // unit sums, needed anyway, tell whether the reference has to move
+              const float us = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+              rowsum += us;
+              big = fmaxf(big, us);
               __align__(16) __half2 h[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(pv[2 * i], pv[2 * i + 1]);
@@ -344,10 +340,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           if (nown == 0 || attempt == 1) break;
-          const bool move = mx > m + lazy;  // (m == -inf: any valid score moves it)
+          // every probability below 2^11 (fp16-safe, and the fp32 sums are far from overflow) unless a unit sum says
+          // otherwise (NaN-safe: inf - inf cannot occur, -inf inputs give 0)
+          const bool move = !(big <= 2048.f);
           if (!__any_sync(0xffffffffu, move)) break;
+          // rare path: the exact block max becomes the reference (one extra read of S), O_wg and l are rescaled.
           // tcgen05.ld / st are warp-collective: every lane takes part, rows that stay use alpha = 1
-          const float alpha = move ? fast_exp2((m - mx) * c2) : 1.f;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_Sown + cc * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = (full || cc * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
+              mx = fmaxf(mx, v);
+            }
+          }
+          const float alpha = move ? fast_exp2((m - mx) * c2) : 1.f;  // (m == -inf: nothing accumulated yet, 0)
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             uint32_t raw[32];

@@ -72,12 +72,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // The slow path backs off with nanosleep between probes and counts iterations instead of reading the clock: ncu showed
 // the plain probe loop (try_wait returns after ~50 cycles; + clock read, compare, branch) taking 40% of ALL issued
 // instructions of the attention kernel — issue slots stolen from the warps doing the exponentials.
-__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, unsigned ns) {
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, unsigned ns, unsigned max_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   unsigned spins = 0;
   for (;;) {
     __nanosleep(ns);
     if (mbar_try_wait(bar, parity)) return;
+    if (ns < max_ns) ns *= 2;  // exponential back-off for waits that are not latency-critical (TMA producers)
     if (++spins > (1u << 26)) {  // >= 2 s
       printf("dfu: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
@@ -85,6 +86,16 @@ __device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, uns
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_ns(bar, parity, 32); }
+// latency-critical single-thread waits (an MMA issuer between two dependent MMAs): probe back to back
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) {
+      printf("dfu: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // same with a suspend-time hint (ns) on the probe itself
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;

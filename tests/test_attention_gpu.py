@@ -67,3 +67,30 @@ def test_attention(ops, planes, B, heads, Nq, Nk, fused):
     err = ((got - ref).abs().max() / ref.abs().max()).item()
     # planes=1: P and the output are rounded to fp16 (2^-11); planes=2: fp32-level (ex2.approx ~2^-22, lo*lo dropped)
     assert err < (1.5e-3 if planes == 1 else 2e-5), err
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_attention_reference_max_moves(ops, planes):
+    """Scores that grow along the key axis (later keys x4, a few x16): the lazy reference max of the softmax has to move
+    several times per row — the rare path that rescales the TMEM accumulator and redoes the block — in the uncut, the
+    automatically cut and the forced-cut distributions."""
+    B, heads, Nq, Nk = 1, 3, 256, 1536
+    C = heads * 64
+    q = _rand((B * Nq, C), 11, 1.5)
+    kv = _rand((B * Nk, 2 * C), 12, 1.5)
+    kv[Nk // 3:, :C] *= 4.0
+    kv[Nk - 100:, :C] *= 4.0
+    q16 = ops.split_f16(q, planes)
+    kv16 = ops.split_f16(kv, planes)
+    qd = q16.double().sum(0).reshape(B, Nq, heads, 64).permute(0, 2, 1, 3)
+    kd = kv16.double().sum(0)[:, :C].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
+    vd = kv16.double().sum(0)[:, C:].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * 0.125, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Nq, C)
+    for ks in (0, 1, 3):
+        out16 = torch.zeros((planes, B * Nq, C), dtype=torch.float16, device="cuda")
+        ops.attention(q16, 0, kv16, 0, kv16, C, B, heads, Nq, Nk, 0.125, out16, kv_splits=ks)
+        torch.cuda.synchronize()
+        got = out16.double().sum(0)
+        assert torch.isfinite(got).all()
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        assert err < (1.5e-3 if planes == 1 else 2e-5), (ks, err)
