@@ -189,31 +189,6 @@ enum : unsigned int {
 };
 
 // ----------------------------------------------------------------------------------------------
-// Grid-wide barrier for grids whose CTAs are all co-resident (the host checks occupancy before choosing a kernel
-// variant that uses it).  bar[0] = arrivals, bar[1] = departures; both are zero between uses — the last CTA to leave
-// resets them — so the same two words serve every launch on the stream.  Call from ONE thread per CTA, bracketed by
-// CTA-level barriers; writes made before it by the CTA are visible to every CTA after it.
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nctas) {
-  __threadfence();
-  atomicAdd(&bar[0], 1u);
-  const long long t0 = clock64();
-  while (*reinterpret_cast<volatile unsigned int*>(&bar[0]) < nctas) {
-    __nanosleep(20);
-    if (clock64() - t0 > 4000000000LL) {
-      printf("dfu: grid barrier timeout block %d\n", blockIdx.x);
-      __trap();
-    }
-  }
-  __threadfence();
-  if (atomicAdd(&bar[1], 1u) == nctas - 1) {
-    bar[0] = 0;
-    bar[1] = 0;
-    __threadfence();
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
 // thread-block clusters: rank, cluster-wide barrier, distributed shared memory loads
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -30,9 +30,7 @@ __device__ __forceinline__ float4 gn_load(const GnSrc& s, int b, int pix, int cq
   return *reinterpret_cast<const float4*>(s.src1 + (static_cast<size_t>(b) * s.HW + pix) * s.C1 + (c - s.C0));
 }
 
-__global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial,
-                                unsigned int* __restrict__ counters, float2* __restrict__ stats, double count,
-                                float eps) {
+__global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __restrict__ partial) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_GN_STATS);
   pdl_wait();
@@ -80,49 +78,6 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int pix_per_cta, float2* __
     __threadfence();
   }
   DFU_TR_END();
-  if (counters == nullptr) return;
-  // The LAST chunk of this sample to finish turns the partials into (mean, rstd): no waiting (an arrival counter, not
-  // a barrier), a fixed summation order (deterministic), and the apply kernel starts from 32 ready numbers.
-  __shared__ int s_last;
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int prev = atomicAdd(&counters[b], 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;
-    if (s_last) counters[b] = 0;  // ready for the next launch
-    __threadfence();
-  }
-  __syncthreads();
-  if (!s_last) return;
-  const int nchunks = gridDim.x;
-  const int nthr = blockDim.x * blockDim.y;
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-  for (int g = warp; g < groups; g += nwarps) {
-    double sum = 0.0, sqd = 0.0;
-    const float2* pp = partial + static_cast<size_t>(b) * nchunks * groups + g;
-    int k = lane;
-    for (; k + 96 < nchunks; k += 128) {
-      const float2 t0 = __ldcg(pp + static_cast<size_t>(k) * groups);
-      const float2 t1 = __ldcg(pp + static_cast<size_t>(k + 32) * groups);
-      const float2 t2 = __ldcg(pp + static_cast<size_t>(k + 64) * groups);
-      const float2 t3 = __ldcg(pp + static_cast<size_t>(k + 96) * groups);
-      sum = (((sum + t0.x) + t1.x) + t2.x) + t3.x;
-      sqd = (((sqd + t0.y) + t1.y) + t2.y) + t3.y;
-    }
-    for (; k < nchunks; k += 32) {
-      const float2 t = __ldcg(pp + static_cast<size_t>(k) * groups);
-      sum += t.x;
-      sqd += t.y;
-    }
-    sum = warp_sum_d(sum);
-    sqd = warp_sum_d(sqd);
-    if (lane == 0) {
-      const double mean = sum / count;
-      double var = sqd / count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[b * groups + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + eps)));
-    }
-  }
 }
 
 // per-(sample, group) mean / rstd from the chunk partials (large maps: thousands of chunks).  One block per
@@ -440,121 +395,6 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnApply a, int U, int q
 }
 
 // =============================================================================================
-// Fused GroupNorm: statistics + grid barrier + apply in ONE launch, the input read ONCE (each thread keeps its
-// <= 4 pixels x 4 channels in registers across the barrier).  Only for grids whose CTAs are all co-resident.
-// =============================================================================================
-template <int PPT>
-__global__ void gn_fused_kernel(GnApply a, float2* __restrict__ partial, unsigned int* __restrict__ sync) {
-  pdl_trigger();
-  extern __shared__ float sm[];  // [TY][2][C]
-  __shared__ float s_mean[64], s_rstd[64];
-  const int C = a.s.C0 + a.s.C1;
-  const int cpg = C / a.groups;
-  const int b = blockIdx.y;
-  const int p0 = blockIdx.x * a.pix_per_cta;
-  const int p1 = min(p0 + a.pix_per_cta, a.s.HW);
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int nthr = blockDim.x * blockDim.y;
-  pdl_wait();
-  float4 vin[PPT];
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int p = p0 + threadIdx.y + j * blockDim.y;
-    vin[j] = (p < p1) ? gn_load(a.s, b, p, threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float sx[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    sx[0] += vin[j].x; sq[0] += vin[j].x * vin[j].x;
-    sx[1] += vin[j].y; sq[1] += vin[j].y * vin[j].y;
-    sx[2] += vin[j].z; sq[2] += vin[j].z * vin[j].z;
-    sx[3] += vin[j].w; sq[3] += vin[j].w * vin[j].w;
-  }
-  const int c = threadIdx.x * 4;
-  float* mine = sm + static_cast<size_t>(threadIdx.y) * 2 * C;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    mine[c + i] = sx[i];
-    mine[C + c + i] = sq[i];
-  }
-  __syncthreads();
-  const int nchunks = gridDim.x;
-  if (tid < a.groups) {
-    float s = 0.f, q = 0.f;
-    for (int ty = 0; ty < static_cast<int>(blockDim.y); ++ty) {
-      const float* row = sm + static_cast<size_t>(ty) * 2 * C;
-      for (int i = 0; i < cpg; ++i) {
-        s += row[tid * cpg + i];
-        q += row[C + tid * cpg + i];
-      }
-    }
-    __stcg(&partial[(static_cast<size_t>(b) * nchunks + blockIdx.x) * a.groups + tid], make_float2(s, q));
-    __threadfence();
-  }
-  __syncthreads();
-  if (tid == 0) grid_barrier(sync, gridDim.x * gridDim.y);
-  __syncthreads();
-  // every CTA combines its sample's chunk partials: warp w takes groups w, w+nwarps, ...; lanes stride the chunks
-  // with independent loads, then a fixed shuffle tree (deterministic)
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-  for (int g = warp; g < a.groups; g += nwarps) {
-    double sum = 0.0, sqd = 0.0;
-    const float2* pp = partial + static_cast<size_t>(b) * nchunks * a.groups + g;
-    int k = lane;
-    for (; k + 96 < nchunks; k += 128) {
-      const float2 t0 = __ldcg(pp + static_cast<size_t>(k) * a.groups);
-      const float2 t1 = __ldcg(pp + static_cast<size_t>(k + 32) * a.groups);
-      const float2 t2 = __ldcg(pp + static_cast<size_t>(k + 64) * a.groups);
-      const float2 t3 = __ldcg(pp + static_cast<size_t>(k + 96) * a.groups);
-      sum = (((sum + t0.x) + t1.x) + t2.x) + t3.x;
-      sqd = (((sqd + t0.y) + t1.y) + t2.y) + t3.y;
-    }
-    for (; k < nchunks; k += 32) {
-      const float2 t = __ldcg(pp + static_cast<size_t>(k) * a.groups);
-      sum += t.x;
-      sqd += t.y;
-    }
-    sum = warp_sum_d(sum);
-    sqd = warp_sum_d(sqd);
-    if (lane == 0) {
-      const double mean = sum / a.count;
-      double var = sqd / a.count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + a.eps));
-    }
-  }
-  __syncthreads();
-  float mu[4], rs[4], ga[4], be[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int g = (c + i) / cpg;
-    mu[i] = s_mean[g];
-    rs[i] = s_rstd[g];
-    ga[i] = a.gamma[c + i];
-    be[i] = a.beta[c + i];
-  }
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int p = p0 + threadIdx.y + j * blockDim.y;
-    if (p >= p1) break;
-    const float4 v = vin[j];
-    float4 y;
-    y.x = (v.x - mu[0]) * rs[0] * ga[0] + be[0];
-    y.y = (v.y - mu[1]) * rs[1] * ga[1] + be[1];
-    y.z = (v.z - mu[2]) * rs[2] * ga[2] + be[2];
-    y.w = (v.w - mu[3]) * rs[3] * ga[3] + be[3];
-    if (a.silu) {
-      y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
-    }
-    const size_t off = (static_cast<size_t>(b) * a.s.HW + p) * C + c;
-    if (a.out16) store_split4(a.out16 + off, a.plane_stride, a.planes, y);
-    if (a.out32) *reinterpret_cast<float4*>(a.out32 + off) = y;
-    if (a.raw16) store_split4(a.raw16 + off, a.plane_stride, a.planes, v);
-  }
-}
-
-// =============================================================================================
 // LayerNorm over the channel dim of [M, C] tokens -> fp16 operand planes.  One warp per token, two-pass in registers.
 // =============================================================================================
 constexpr int kLnMaxQuads = 10;  // C <= 1280
@@ -820,50 +660,11 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
     }
   }
   const size_t stats_smem = static_cast<size_t>(ty) * 2 * C * sizeof(float);
-  // measured on B200 (in-graph, 64x64x320): fused 15.9 us vs stats+apply 12.3 us — the grid barrier costs more than
-  // the launch it saves, so the single-launch variant is opt-in (DFU_GN_FUSED=1)
-  static const bool fused_ok = getenv("DFU_GN_FUSED") && getenv("DFU_GN_FUSED")[0] == '1';
-  if (sync_words && fused_ok) {
-    // one launch, one read of the input, when the whole grid is co-resident: pick the fewest pixels per thread
-    // (most CTAs) that still fits the GPU in one wave
-    GnApply f;
-    f.s = s; f.groups = groups; f.stats = nullptr;
-    f.partial = static_cast<const float2*>(workspace);
-    f.count = static_cast<double>(C / groups) * HW;
-    f.gamma = gamma; f.beta = beta; f.eps = eps; f.silu = silu;
-    f.out16 = static_cast<__half*>(out16); f.planes = planes; f.plane_stride = plane_stride;
-    f.out32 = out32; f.raw16 = static_cast<__half*>(raw16);
-    const int sms = num_sms() > 0 ? num_sms() : 148;
-    auto try_fused = [&](auto kernel, int ppt) -> int {
-      const int fppc = ty * ppt;
-      const int fchunks = (HW + fppc - 1) / fppc;
-      if (fchunks > chunks) return 1;  // partial buffer is sized for the unfused geometry
-      int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C4 * ty, stats_smem) != cudaSuccess) return 1;
-      if (static_cast<long long>(fchunks) * B > static_cast<long long>(per_sm) * sms) return 1;
-      f.pix_per_cta = fppc;
-      f.nchunks = fchunks;
-      cudaError_t e = launch_k(kernel, dim3(fchunks, B), dim3(block), stats_smem, stream, f,
-                               static_cast<float2*>(workspace), static_cast<unsigned int*>(sync_words));
-      if (e != cudaSuccess) {
-        set_error("groupnorm fused launch failed: %s", cudaGetErrorString(e));
-        return -1;
-      }
-      return 0;
-    };
-    int r = try_fused(gn_fused_kernel<4>, 4);
-    if (r == 1) r = try_fused(gn_fused_kernel<8>, 8);
-    if (r == 1) r = try_fused(gn_fused_kernel<16>, 16);
-    if (r == 0) return DFU_OK;
-    if (r < 0) return DFU_ERR_CUDA;
-  }
-  // statistics; with arrival counters available the last chunk of each sample also finalises (mean, rstd)
-  float2* stats_out = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
-  // measured on B200: letting the last statistics CTA finalise costs more (0.95 vs 0.69 ms of GroupNorm per UNet
-  // step: a serial tail on the critical path) than combining the partials in every apply CTA's prologue -> opt-in
-  static const bool last_cta = getenv("DFU_GN_LASTCTA") && getenv("DFU_GN_LASTCTA")[0] == '1';
-  unsigned int* counters = (last_cta && sync_words && B <= 48) ? static_cast<unsigned int*>(sync_words) + 8 : nullptr;
-  DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), stats_smem, stream, s, groups, ppc, static_cast<float2*>(workspace), counters, stats_out, static_cast<double>(C / groups) * HW, eps));
+  // Two-launch path (maps too large for the cluster kernel).  Built, measured in the captured step and removed: a
+  // single-launch grid-barrier variant (15.9 vs 12.3 us at 64x64x320: the barrier costs more than the launch it
+  // saves) and letting the last-arriving statistics CTA finalise (mean, rstd) (0.95 vs 0.69 ms of GroupNorm per UNet
+  // step: a serial tail on the critical path).
+  DFU_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(grid), dim3(block), stats_smem, stream, s, groups, ppc, static_cast<float2*>(workspace)));
   GnApply a;
   a.s = s;
   a.groups = groups;
@@ -871,9 +672,9 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   a.partial = static_cast<const float2*>(workspace);
   a.nchunks = chunks;
   a.count = static_cast<double>(C / groups) * HW;
-  a.stats = counters ? stats_out : nullptr;
+  a.stats = nullptr;
   const bool inline_finalize = chunks <= 256 && static_cast<int>(block.x * block.y) >= 8 * groups;
-  if (!counters && !inline_finalize) {
+  if (!inline_finalize) {
     float2* stats = static_cast<float2*>(workspace) + static_cast<size_t>(B) * chunks * groups;
     DFU_CHECK_CUDA(launch_k(gn_finalize_kernel, dim3(groups, B), dim3(256), 0, stream, static_cast<const float2*>(workspace), chunks, groups, a.count, eps, stats));
     a.stats = stats;

@@ -100,8 +100,8 @@ typedef struct DfuGemm {
   int32_t stages;
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
   size_t workspace_bytes;
-  void* sync_words;        /* optional: 2 x uint32, ZERO on entry (left zero): lets a split-K launch whose CTAs are all
-                              co-resident run its second stage in the same kernel behind a grid barrier */
+  void* sync_words;        /* reserved (accepted and ignored): backed a grid-barrier second stage that was measured
+                              slower than the PDL-overlapped reduce launch and removed */
 } DfuGemm;
 
 int dfu_gemm(const DfuGemm* desc, void* stream);
@@ -120,9 +120,9 @@ size_t dfu_gemm_workspace(const DfuGemm* desc);
  * Writes any of: normalised(+SiLU) fp16 operand `out16`, the same in fp32 `out32` (feeds the few-channel
  * fp32 output convs), and `raw16`, the un-normalised cast of the input (operand of the 1x1 conv_shortcut).
  * workspace: dfu_groupnorm_workspace() bytes of per-chunk partial sums (deterministic two-stage reduction).
- * sync_words: optional (8 + B) x uint32, ZERO on entry (left zero): words [8, 8+B) are per-sample arrival counters
- * that let the last statistics CTA of a sample finalise (mean, rstd) so the apply kernel starts from ready numbers;
- * words [0,2) back the opt-in single-launch variant (DFU_GN_FUSED=1).
+ * Small and medium maps run ONE launch (thread-block clusters, statistics exchanged through distributed shared memory,
+ * the input read once); larger maps run a statistics launch + an apply launch.  sync_words: reserved (accepted and
+ * ignored; it backed grid-barrier / arrival-counter variants that were measured slower and removed).
  */
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups);
 int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, int groups,
