@@ -109,7 +109,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
   return ok != 0;
 }
 // Long waits (epilogue warps waiting for the whole main loop): coarser back-off
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait_ns(bar, parity, 200); }
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait_ns(bar, parity, 64); }
 
 // ----------------------------------------------------------------------------------------------
 // programmatic dependent launch: every kernel lets its successor start launching at once (its CTAs only fill
