@@ -120,6 +120,7 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
   DFU_TR_MARK(6);
   const int pix0 = blockIdx.x * kSmallInPix;  // pixel indices fit 32 bits (checked by the host): no 64-bit divisions
   const int npix = B * H * W;
+#pragma unroll 4  // independent gathers: let four loads be in flight per thread instead of one
   for (int i = threadIdx.x; i < kSmallInPix * K; i += blockDim.x) {
     const int k = i / kSmallInPix, pl = i % kSmallInPix;  // consecutive threads -> consecutive pixels (coalesced NCHW)
     const int pix = pix0 + pl;
