@@ -200,7 +200,7 @@ struct SmallOut {
 };
 
 template <bool kSmemW>
-__global__ void __launch_bounds__(256, 2) conv_small_out_kernel(SmallOut p) {
+__global__ void __launch_bounds__(256, kSmemW ? 2 : 4) conv_small_out_kernel(SmallOut p) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_CONV_OUT);
   // The packed weights ([Cout][k*k][Cin], up to ~150 KB) are constants: each CTA copies them to shared memory ONCE,
@@ -232,27 +232,48 @@ __global__ void __launch_bounds__(256, 2) conv_small_out_kernel(SmallOut p) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // all taps of a channel quad are requested before the first FMA: one memory latency per quad, not one per tap
-    const float* xrow[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int iy = y + t / p.ksz - pad, ix = x + t % p.ksz - pad;
-      const bool ok = t < kk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-      xrow[t] = ok ? p.x + ((static_cast<size_t>(b) * p.H + iy) * p.W + ix) * p.Cin : nullptr;
-    }
-    for (int q = lane; q < C4; q += 32) {
-      float4 xv[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-        xv[t] = xrow[t] ? reinterpret_cast<const float4*>(xrow[t])[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kSmemW) {
+      // (many pixels per warp, few warps per SM) all taps of a channel quad are requested before the first FMA: one
+      // memory latency per quad, not one per tap
+      const float* xrow[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        if (t < kk) {
+        const int iy = y + t / p.ksz - pad, ix = x + t % p.ksz - pad;
+        const bool ok = t < kk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        xrow[t] = ok ? p.x + ((static_cast<size_t>(b) * p.H + iy) * p.W + ix) * p.Cin : nullptr;
+      }
+      for (int q = lane; q < C4; q += 32) {
+        float4 xv[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          xv[t] = xrow[t] ? reinterpret_cast<const float4*>(xrow[t])[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (t < kk) {
+#pragma unroll
+            for (int co = 0; co < 8; ++co) {
+              if (co < p.Cout) {
+                const float4 wv = *(reinterpret_cast<const float4*>(wbase + (static_cast<size_t>(co) * kk + t) * p.Cin) + q);
+                acc[co] += wv.x * xv[t].x + wv.y * xv[t].y + wv.z * xv[t].z + wv.w * xv[t].w;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // (one pixel per warp, every warp of the grid resident at once: latency is hidden by occupancy, so the loop
+      // stays small — 64 registers; the batched form above needs 128 and ran this shape in two waves, 48 vs 11 us)
+      for (int t = 0; t < kk; ++t) {
+        const int iy = y + t / p.ksz - pad, ix = x + t % p.ksz - pad;
+        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + ((static_cast<size_t>(b) * p.H + iy) * p.W + ix) * p.Cin);
+        for (int q = lane; q < C4; q += 32) {
+          const float4 xv = xr[q];
 #pragma unroll
           for (int co = 0; co < 8; ++co) {
             if (co < p.Cout) {
-              const float4 wv = *(reinterpret_cast<const float4*>(wbase + (static_cast<size_t>(co) * kk + t) * p.Cin) + q);
-              acc[co] += wv.x * xv[t].x + wv.y * xv[t].y + wv.z * xv[t].z + wv.w * xv[t].w;
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(co) * kk + t) * p.Cin) + q);
+              acc[co] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
             }
           }
         }
