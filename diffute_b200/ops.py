@@ -219,11 +219,12 @@ def image_operand(op, a16: torch.Tensor, w16: torch.Tensor, planes: int, taps, i
 
 
 # ---------------------------------------------------------------------------------------------
-# per-shape tiling table (measured on B200 by scripts/tune_gemm.py; the C cost model is the fallback)
+# per-shape tiling table (measured on B200 inside the captured step by scripts/tune_insitu.py; the C cost model is the
+# fallback for shapes the table does not hold)
 # ---------------------------------------------------------------------------------------------
 TUNE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning_b200.json")
 TUNE_TABLE = {}
-TUNER = None  # set to a callable (d, ws, key) -> (block_n, splits, stages) by scripts/tune_gemm.py
+TUNER = None  # optional hook: a callable (d, ws, key) -> (block_n, splits, stages) consulted for shapes not in the table
 if os.path.exists(TUNE_PATH):
     try:
         with open(TUNE_PATH) as _f:
