@@ -101,6 +101,7 @@ SIGNATURES = {
     "dfu_gaussian_sample": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "dfu_softmax_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _i, _i, _i64, _vp]),
     "dfu_attention_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "dfu_attention_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int32)]),
     "dfu_attention": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _i, _i64,
                            _i, _vp, _sz, _vp]),
     "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _i64, _vp]),

@@ -568,6 +568,31 @@ static int attn_grid(int B, int heads, int Nq, int Nk, int kv_splits) {
   return static_cast<int>(G);
 }
 
+// Host-side view of the stream-K distribution (no GPU needed): out[0] = G (CTAs), out[1] = work items, out[2] = 64-key
+// blocks per item, out[3] = largest number of pieces any item is cut into, out[4] = 1 if every CTA range is non-empty
+// and attn_cta_of inverts attn_range_begin on every range boundary.
+extern "C" int dfu_attention_plan(int B, int heads, int Nq, int Nk, int kv_splits, int32_t* out) {
+  if (!out || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return DFU_ERR_INVALID;
+  AttnParams p;
+  p.q_tiles = (Nq + kBQ - 1) / kBQ;
+  p.nblk = (Nk + kBKV - 1) / kBKV;
+  p.items = p.q_tiles * heads * B;
+  p.total = static_cast<long long>(p.items) * p.nblk;
+  p.G = attn_grid(B, heads, Nq, Nk, kv_splits);
+  int max_pieces = 0, ok = 1;
+  for (int c = 0; c < p.G; ++c) {
+    const long long b0 = attn_range_begin(p, c), b1 = attn_range_begin(p, c + 1);
+    if (b0 >= b1 || attn_cta_of(p, b0) != c || attn_cta_of(p, b1 - 1) != c) ok = 0;
+  }
+  for (int i = 0; i < p.items; ++i) {
+    const long long u0 = static_cast<long long>(i) * p.nblk;
+    const int pieces = attn_cta_of(p, u0 + p.nblk - 1) - attn_cta_of(p, u0) + 1;
+    if (pieces > max_pieces) max_pieces = pieces;
+  }
+  out[0] = p.G; out[1] = p.items; out[2] = p.nblk; out[3] = max_pieces; out[4] = ok;
+  return DFU_OK;
+}
+
 extern "C" size_t dfu_attention_workspace(int B, int heads, int Nq, int Nk, int kv_splits) {
   const int q_tiles = (Nq + kBQ - 1) / kBQ;
   const int G = attn_grid(B, heads, Nq, Nk, kv_splits);

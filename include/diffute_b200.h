@@ -191,6 +191,9 @@ int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int ld_in,
  * the pieces in key order (deterministic, bit-identical run to run).
  */
 size_t dfu_attention_workspace(int B, int heads, int Nq, int Nk, int kv_splits);
+/* The distribution dfu_attention would use (no GPU needed): out[5] = {CTAs, work items, 64-key blocks per item, largest
+ * number of pieces an item is cut into (<= 8), 1 if the range <-> CTA maps are consistent}. */
+int dfu_attention_plan(int B, int heads, int Nq, int Nk, int kv_splits, int32_t* out);
 int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, const void* k, int ldk, int k_col0,
                   const void* v, int ldv, int v_col0, int64_t kv_plane_stride, int B, int heads, int Nq, int Nk,
                   int planes, float scale, void* out, int ldo, int64_t out_plane_stride, int kv_splits,

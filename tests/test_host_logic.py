@@ -195,3 +195,30 @@ def test_engine_fails_loudly_without_cuda():
     assert "oracle" not in "".join(open(os.path.join(ROOT, "diffute_b200", f)).read()
                                    for f in os.listdir(os.path.join(ROOT, "diffute_b200"))
                                    if f.endswith(".py")).replace("the oracle", "").replace("CPU oracle", "")
+
+
+def test_attention_streamk_plan_invariants():
+    """dfu_attention_plan (host arithmetic only): every CTA gets a non-empty contiguous range of key-block units, the
+    unit -> CTA map inverts the range map, no item is cut into more pieces than the merge kernel holds (8), an explicit
+    kv_splits = 1 never cuts, and the UNet shapes get the distribution DESIGN.md describes."""
+    import ctypes as C
+    from diffute_b200 import _lib
+    L = _lib.lib()
+    out = (C.c_int32 * 5)()
+    shapes = [(1, 5, 4096, 4096), (1, 5, 4096, 577), (1, 10, 1024, 1024), (1, 10, 1024, 577), (1, 20, 256, 256),
+              (1, 20, 256, 577), (1, 20, 64, 64), (1, 20, 64, 577), (8, 5, 9216, 9216), (2, 5, 4096, 577),
+              (1, 2, 64, 4096), (1, 2, 200, 130), (3, 7, 130, 1500), (1, 1, 1, 1), (1, 1, 128, 65)]
+    for B, h, Nq, Nk in shapes:
+        for ks in (0, 1, 2, 3, 5, 64):
+            assert L.dfu_attention_plan(B, h, Nq, Nk, ks, out) == 0
+            G, items, nblk, pieces, ok = list(out)
+            assert ok == 1, (B, h, Nq, Nk, ks)
+            assert items == B * h * -(-Nq // 128) and nblk == -(-Nk // 64)
+            assert items <= G <= items * nblk and pieces <= 8, (B, h, Nq, Nk, ks, G, pieces)
+            if ks == 1:
+                assert G == items and pieces == 1
+    # level-0 self-attention at 64x64 latents: two CTAs per SM when a device is visible, else the 148-SM default
+    L.dfu_attention_plan(1, 5, 4096, 4096, 0, out)
+    assert out[0] in (2 * 148, 2 * max(L.dfu_num_sms(), 1))
+    L.dfu_attention_plan(1, 5, 4096, 577, 0, out)   # 577 glyph tokens: never cut
+    assert out[0] == out[1] == 160 and out[3] == 1
