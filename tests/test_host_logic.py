@@ -222,3 +222,41 @@ def test_attention_streamk_plan_invariants():
     assert out[0] in (2 * 148, 2 * max(L.dfu_num_sms(), 1))
     L.dfu_attention_plan(1, 5, 4096, 577, 0, out)   # 577 glyph tokens: never cut
     assert out[0] == out[1] == 160 and out[3] == 1
+
+
+def test_gemm_plan_tilings_without_gpu():
+    """dfu_gemm_plan (host arithmetic only): the tiling the library would launch for representative shapes — stage ring
+    within the shared-memory budget, FP16X2 counting k-blocks once (its three products share a stage), explicit
+    tilings honoured, illegal ones refused, block_n multiples of 16 accepted (32 for GEGLU)."""
+    import ctypes as C
+    from diffute_b200 import _lib
+    L = _lib.lib()
+    out = (C.c_int32 * 6)()
+
+    def plan(m, n, k, npass=1, conv=0, hw=None, epi=0, tune=(0, 0, 0), taps=1):
+        d = _lib.Gemm()
+        d.m, d.n, d.ngroups, d.npass, d.epi = m, n, 1, npass, epi
+        d.g[0].ntaps, d.g[0].k_per_tap = taps, k
+        if conv:
+            d.conv, d.B, d.H, d.W = 1, 1, hw, hw
+            d.g[0].a_mode, d.g[0].a_c = 1, k
+        d.block_n, d.splits, d.stages = tune
+        rc = L.dfu_gemm_plan(C.byref(d), out)
+        return rc, list(out)
+
+    for m, n, k, taps, conv, hw in [(4096, 320, 320, 1, 0, None), (4096, 320, 320, 9, 1, 64), (1024, 640, 640, 9, 1, 32),
+                                    (256, 1280, 1280, 9, 1, 16), (64, 1280, 1280, 9, 1, 8), (4096, 2560, 320, 1, 0, None),
+                                    (262144, 128, 128, 9, 1, 512)]:
+        for npass in (1, 3):
+            rc, (bn, sp, st, tm, tn, kb) = plan(m, n, k, npass, conv, hw, taps=taps)
+            assert rc == 0, L.dfu_last_error()
+            assert kb == taps * k // 64                      # k-blocks counted once, also for the 3-pass mode
+            assert bn % 16 == 0 and n % bn == 0 and tn == n // bn and tm == -(-m // 128)
+            assert 1 <= sp <= kb and 2 <= st <= 12
+            stage = (2 if npass == 3 else 1) * (16384 + bn * 128)
+            assert st * stage + 1024 <= 224 * 1024           # ring + alignment slack inside the dynamic smem budget
+    assert plan(4096, 320, 320, tune=(80, 1, 4))[1][:3] == [80, 1, 4]     # block_n = 80 is a legal UMMA N
+    assert plan(4096, 320, 320, tune=(160, 9, 3))[1][1] == 5              # more splits than k-blocks: clamped
+    assert plan(4096, 320, 320, tune=(48, 1, 3))[0] == -1                  # does not divide n
+    assert plan(4096, 2560, 320, epi=2, tune=(80, 1, 3))[0] == -1          # GEGLU pairs value/gate columns in 32s
+    assert plan(4096, 320, 320, npass=3, tune=(160, 1, 12))[1][2] < 12    # 12 double-size stages do not fit: clamped
