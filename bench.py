@@ -98,72 +98,83 @@ class ClockSampler:
 # =================================================================================================
 # CPU arm: the restated reference path on the host cores
 # =================================================================================================
-def cpu_reference_sample(threads=None, unet_reps=1):
-    """Bounded sample of BASELINE config 2 on the CPU oracle: `unet_reps` UNet steps (64x64 latent) + one VAE encode +
-    one VAE decode at 512x512, extrapolated to 50 steps.  Returns (images_per_s, detail dict)."""
-    import torch
-    from diffute_b200 import arch, synthetic
-    from oracle import UNetOracle, VAEOracle
-    threads = threads or _cpu_threads()
-    torch.set_num_threads(threads)
-    u, v = UNetOracle(), VAEOracle()
-    u.load_state_dict(synthetic.make_state_dict(arch.unet_param_shapes()))
-    v.load_state_dict(synthetic.make_state_dict(arch.vae_param_shapes()))
-    inp = synthetic.make_inputs(1, PX, PX)
-    x = torch.cat([inp["latents"], inp["mask"][:, :, ::8, ::8], inp["latents"]], 1)
-    t_u = []
-    for _ in range(unet_reps):
+class CpuArm:
+    """The restated reference path (oracle/) on the host cores: BASELINE config 2 cut into bounded pieces.
+
+    One CPU "step" is ONE UNet forward at the 64x64 latent (1/50 of an image's loop); the VAE encode + decode at
+    512x512 is timed once.  images/s is then 1 / (50 x median(UNet step) + VAE) — an extrapolation, reported as such;
+    `ms_per_step` of the reference line is what one timed step really took.  Both the in-process `cpu_baseline` leg and
+    `--impl reference` go through this class (same threads, same warm-up, same median) so that they agree."""
+
+    def __init__(self, threads=None):
+        import torch
+        from diffute_b200 import arch, synthetic
+        from oracle import UNetOracle, VAEOracle
+        self.torch = torch
+        self.threads = threads or _cpu_threads()
+        torch.set_num_threads(self.threads)
+        self.u, self.v = UNetOracle(), VAEOracle()
+        self.u.load_state_dict(synthetic.make_state_dict(arch.unet_param_shapes()))
+        self.v.load_state_dict(synthetic.make_state_dict(arch.vae_param_shapes()))
+        self.inp = synthetic.make_inputs(1, PX, PX)
+        self.x = torch.cat([self.inp["latents"], self.inp["mask"][:, :, ::8, ::8], self.inp["latents"]], 1)
+
+    def unet_step(self) -> float:
         t0 = time.perf_counter()
-        u(x, 981, inp["glyph_embeds"])
-        t_u.append(time.perf_counter() - t0)
-    t0 = time.perf_counter()
-    z = v.encode(inp["masked_image"]).latent_dist.mode()
-    t_enc = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    v.decode(z)
-    t_dec = time.perf_counter() - t0
+        with self.torch.no_grad():
+            self.u(self.x, 981, self.inp["glyph_embeds"])
+        return time.perf_counter() - t0
+
+    def vae(self):
+        with self.torch.no_grad():
+            t0 = time.perf_counter()
+            z = self.v.encode(self.inp["masked_image"]).latent_dist.mode()
+            t1 = time.perf_counter()
+            self.v.decode(z)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    @staticmethod
+    def images_per_s(unet_step_s, vae_s):
+        return 1.0 / (NSTEPS * unet_step_s + vae_s)
+
+
+def cpu_reference_sample(threads=None, unet_reps=3, warmup=1):
+    """Bounded sample for the `cpu_baseline` key: `warmup` + `unet_reps` UNet steps and one VAE encode + decode."""
+    arm = CpuArm(threads)
+    for _ in range(warmup):
+        arm.unet_step()
+    t_u = [arm.unet_step() for _ in range(unet_reps)]
+    t_enc, t_dec = arm.vae()
     tu = statistics.median(t_u)
-    total = NSTEPS * tu + t_enc + t_dec
-    return 1.0 / total, dict(unet_step_s=tu, vae_encode_s=t_enc, vae_decode_s=t_dec, image_s_extrapolated=total,
-                             cores=threads)
+    return arm.images_per_s(tu, t_enc + t_dec), dict(unet_step_s=tu, vae_encode_s=t_enc, vae_decode_s=t_dec,
+                                                       image_s_extrapolated=NSTEPS * tu + t_enc + t_dec,
+                                                       cores=arm.threads, unet_reps=unet_reps)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    threads = _cpu_threads()
-    from diffute_b200 import arch, synthetic
-    from oracle import UNetOracle, VAEOracle
-    torch.set_num_threads(threads)
-    u, v = UNetOracle(), VAEOracle()
-    u.load_state_dict(synthetic.make_state_dict(arch.unet_param_shapes()))
-    v.load_state_dict(synthetic.make_state_dict(arch.vae_param_shapes()))
-    inp = synthetic.make_inputs(1, PX, PX)
-    x = torch.cat([inp["latents"], inp["mask"][:, :, ::8, ::8], inp["latents"]], 1)
-    # VAE encode + decode measured once (warm-up leg); every timed step = one UNet forward, extrapolated
-    t0 = time.perf_counter()
-    z = v.encode(inp["masked_image"]).latent_dist.mode()
-    v.decode(z)
-    t_vae = time.perf_counter() - t0
-    for _ in range(max(args.warmup - 1, 0)):
-        u(x, 981, inp["glyph_embeds"])
-    ts = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        u(x, 981, inp["glyph_embeds"])
-        ts.append(time.perf_counter() - t0)
-    per_image = NSTEPS * (sum(ts) / len(ts)) + t_vae
-    val = 1.0 / per_image
-    sample = (f"per step: 1 UNet forward (64x64 latent, B=1) on the fp32 CPU oracle, x{NSTEPS} + one VAE encode+decode "
-              f"at 512x512 measured once ({t_vae:.1f} s); extrapolated to one 50-step image")
+    arm = CpuArm()
+    t_enc, t_dec = arm.vae()               # once, outside the timed steps (it is 1/50th as frequent as a UNet step)
+    for _ in range(max(args.warmup, 1)):
+        arm.unet_step()
+    ts = [arm.unet_step() for _ in range(args.steps)]
+    tu = statistics.median(ts)
+    val = arm.images_per_s(tu, t_enc + t_dec)
+    sample = (f"{args.steps} timed steps, each ONE UNet forward (64x64 latent, B=1) on the fp32 CPU oracle (median "
+              f"{tu:.3f} s); VAE encode {t_enc:.2f} s + decode {t_dec:.2f} s at 512x512 measured once; images/s = "
+              f"1 / ({NSTEPS} x median UNet step + VAE), i.e. extrapolated from 1/{NSTEPS} of the loop per step")
     line = {"impl": "reference", "metric": "images/sec at 512x512, 50 DDIM steps", "value": val, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_image * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": sum(ts) / len(ts) * 1e3,
+            "ms_per_step_is": "one timed CPU step = one UNet forward (1/50 of an image's loop), as measured",
+            "image_ms_extrapolated": (NSTEPS * tu + t_enc + t_dec) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "512x512 glyph-conditioned inpaint, 50 DDIM steps, batch 1 (BASELINE config 2)",
                        "arm": "CPU restatement of the reference's diffusers path (oracle/), torch fp32"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": arm.threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -173,7 +184,125 @@ def run_reference(args):
 # =================================================================================================
 # GPU arm
 # =================================================================================================
+class _AblatingLib:
+    """Timing ablation (this file only): a proxy over the CDLL whose ablated entry points are no-ops, installed by
+    swapping `ops.lib` while a step is re-captured.  Results of an ablated step are garbage; only its duration is used."""
+    CLASSES = {"dfu_gemm": "gemm", "dfu_attention": "attention", "dfu_groupnorm": "groupnorm",
+               "dfu_layernorm": "layernorm"}
+
+    def __init__(self, real, ablate):
+        self._real, self._ablate = real, set(ablate)
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if self.CLASSES.get(name) in self._ablate:
+            return lambda *a: 0
+        return fn
+
+
+def _event_ms(fn, n):
+    import torch
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def extra_configs(pipe, dev, peaks):
+    """BASELINE configs 3 (1-GPU leg: batch 8), 4 (VAE encode+decode, batch 32) and 5 (768x768, batch 4, CFG x2), each
+    with its own roofline sub-record.  Inputs are resident in HBM; CUDA events on the launch stream; one warm-up call,
+    two timed calls (each call is seconds of GPU work — far beyond L2, no flush needed)."""
+    import torch
+    from diffute_b200 import synthetic
+    out = {}
+    tf = peaks["tflops"]
+
+    def dev_inputs(B, px, seed=0):
+        inp = synthetic.make_inputs(B, px, px, seed=seed)
+        return {k: v.to(dev) for k, v in inp.items()}
+
+    # ---- config 3, single-GPU leg: 512x512, 50 steps, batch 8 ------------------------------------------------
+    B = 8
+    d = dev_inputs(B, PX)
+    call = lambda: pipe(masked_image=d["masked_image"], mask_image=d["mask"], glyph_embeds=d["glyph_embeds"],
+                        latents=d["latents"], posterior_noise=d["posterior_noise"], num_inference_steps=NSTEPS).images
+    call()
+    ms = _event_ms(call, 2)
+    graph, _, _ = pipe._step_graph(B, PX // 8, PX // 8, True)
+    graph.replay()
+    step_ms = _event_ms(graph.replay, 10)
+    step_tf = (UNET_GFLOP - UNET_CTX_GFLOP) * B / 1e3 / (step_ms / 1e3)
+    out["config3_b8_1gpu"] = {
+        "workload": "512x512, 50 DDIM steps, batch 8 on ONE GPU (BASELINE config 3, single-GPU leg)",
+        "images_per_s": B / (ms / 1e3), "ms_per_batch": ms, "unet_step_ms": step_ms,
+        "roofline": {"bound": "tensor", "achieved": step_tf, "peak": tf, "unit": "TFLOP/s", "frac": step_tf / tf,
+                     "what": "whole UNet step at B=8 (all kernels): algorithmic FLOP / graph-replay time",
+                     "per_layer_roofline_ms": 4.411, "frac_of_per_layer_roofline": 4.411 / step_ms}}
+    del d
+
+    # ---- config 4: AutoencoderKL encode + decode, 512x512, batch 32 -------------------------------------------
+    B = 32
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand((B, 3, PX, PX), generator=g) * 2 - 1).to(dev)
+    vae = pipe.vae
+    enc = lambda: vae.encode(x).latent_dist.mode()
+    z = enc()
+    dec = lambda: vae.decode(z).sample
+    dec()
+    rt = lambda: vae(x)["sample"]
+    t_enc, t_dec, t_rt = _event_ms(enc, 2), _event_ms(dec, 2), _event_ms(rt, 2)
+    enc_tf = VAE_ENC_GFLOP * B / 1e3 / (t_enc / 1e3)
+    dec_tf = VAE_DEC_GFLOP * B / 1e3 / (t_dec / 1e3)
+    out["config4_vae_b32"] = {
+        "workload": "AutoencoderKL encode + decode, 512x512, batch 32, one GPU (BASELINE config 4)",
+        "encode_images_per_s": B / (t_enc / 1e3), "decode_images_per_s": B / (t_dec / 1e3),
+        "roundtrip_images_per_s": B / (t_rt / 1e3), "encode_ms": t_enc, "decode_ms": t_dec, "roundtrip_ms": t_rt,
+        "precision": {"encoder": "fp16" if vae.enc_prec == 1 else "fp16x2 (3 tensor passes)",
+                      "decoder": "fp16" if vae.dec_prec == 1 else "fp16x2 (3 tensor passes)"},
+        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": tf,
+                     "encode": {"achieved": enc_tf, "frac": enc_tf / tf, "per_layer_roofline_ms": 22.97},
+                     "decode": {"achieved": dec_tf, "frac": dec_tf / tf, "per_layer_roofline_ms": 51.68},
+                     "what": "algorithmic FLOP (each contraction counted once, whatever the pass count) / time"}}
+    del x, z
+
+    # ---- config 5: 768x768, batch 4, classifier-free guidance x2 (UNet batch 8 at 96x96 latents) ---------------
+    B, px = 4, 768
+    d = dev_inputs(B, px)
+    neg = torch.randn((B, 577, 1024), generator=torch.Generator().manual_seed(11)).to(dev)
+    call = lambda: pipe(masked_image=d["masked_image"], mask_image=d["mask"], glyph_embeds=d["glyph_embeds"],
+                        negative_glyph_embeds=neg, guidance_scale=2.0, latents=d["latents"],
+                        posterior_noise=d["posterior_noise"], num_inference_steps=NSTEPS).images
+    call()
+    ms = _event_ms(call, 2)
+    graph, _, _ = pipe._step_graph(2 * B, px // 8, px // 8, False)
+    graph.replay()
+    step_ms = _event_ms(graph.replay, 5)
+    step_tf = (2226.91 - UNET_CTX_GFLOP) * 2 * B / 1e3 / (step_ms / 1e3)
+    img_gflop = 2 * NSTEPS * (2226.91 - UNET_CTX_GFLOP) + 2 * UNET_CTX_GFLOP + 2609.12 + 5754.30
+    out["config5_768_b4_cfg"] = {
+        "workload": "768x768, 50 DDIM steps, batch 4, classifier-free guidance x2 (BASELINE config 5)",
+        "images_per_s": B / (ms / 1e3), "ms_per_batch": ms, "unet_step_ms_batch8_96x96": step_ms,
+        "image_tflops": img_gflop * B / 1e3 / (ms / 1e3),
+        "roofline": {"bound": "tensor", "achieved": step_tf, "peak": tf, "unit": "TFLOP/s", "frac": step_tf / tf,
+                     "what": "whole UNet step at UNet-batch 8, 96x96 latents: algorithmic FLOP / graph-replay time",
+                     "per_layer_roofline_ms": 11.422, "frac_of_per_layer_roofline": 11.422 / step_ms}}
+    return out
+
+
 def run_gpu(args):
+    # The CPU leg runs first, in a fresh process state (no CUDA context, no process group) — the same conditions as
+    # `--impl reference` — and only at N=1: under torchrun the other ranks would spin in a barrier while rank 0 computes.
+    cpu = None
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
+        v_cpu, det = cpu_reference_sample()
+        cpu = {"value": v_cpu, "unit": "images/s", "cores": det["cores"], "kind": "port",
+               "sample": (f"{det['unet_reps']} UNet steps after 1 warm-up (median {det['unet_step_s']:.2f} s) + 1 VAE "
+                          f"encode ({det['vae_encode_s']:.1f} s) + 1 VAE decode ({det['vae_decode_s']:.1f} s) at 512x512 "
+                          f"on the fp32 CPU oracle, extrapolated to 50 steps")}
     import torch
     from diffute_b200 import arch, dist as ddist, ops, synthetic
     from diffute_b200.pipeline import DiffUTEPipeline
@@ -281,8 +410,11 @@ def run_gpu(args):
     # In-graph cost of each kernel class by ablation: replay the captured step with that class's launches removed
     # (same buffers, same order, PDL edges intact) and take the difference — CUDA events on the replay stream, no
     # per-launch event overhead.  This is the duration used for the roofline.
+    real_lib = ops.lib
+
     def graph_ms(ablate):
-        ops.ABLATE = set(ablate)
+        if ablate:
+            ops.lib = lambda: _AblatingLib(real_lib(), ablate)
         try:
             pipe.unet._forward_impl(B, h, w, srcs=srcs, t=state[:B])
             torch.cuda.synchronize()
@@ -290,7 +422,7 @@ def run_gpu(args):
             with torch.cuda.graph(gr):
                 pipe.unet._forward_impl(B, h, w, srcs=srcs, t=state[:B])
         finally:
-            ops.ABLATE = set()
+            ops.lib = real_lib
         gr.replay()
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,13 +469,9 @@ def run_gpu(args):
     # through the Python wrappers, which only counted the eager ones (VAE, context projections, scheduler state)
     gpu_launches = eager_launches + args.steps * NSTEPS * launches_per_unet_step
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        v_cpu, det = cpu_reference_sample(unet_reps=2)
-        cpu = {"value": v_cpu, "unit": "images/s", "cores": det["cores"], "kind": "port",
-               "sample": (f"2 UNet steps (median {det['unet_step_s']:.2f} s) + 1 VAE encode ({det['vae_encode_s']:.1f} s) "
-                          f"+ 1 VAE decode ({det['vae_decode_s']:.1f} s) at 512x512 on the fp32 CPU oracle, "
-                          f"extrapolated to 50 steps")}
+    configs = None
+    if world == 1 and not args.no_extra_configs:
+        configs = extra_configs(pipe, dev, peaks)
     if rank == 0:
         line = {"metric": "images/sec at 512x512, 50 DDIM steps", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_res / args.steps * 1e3,
@@ -356,12 +484,12 @@ def run_gpu(args):
                                        f"{B} image(s) per GPU, batch sharded over GPUs with no per-step collective",
                            "global_batch": B * world, "precision": args.precision,
                            "l2": "working set (1.9-3.8 GB of packed weights per step) exceeds the 126 MB L2",
-                           "parity": "decoded RGB vs fp32 CPU oracle at this exact workload: max rel err 3.0e-4 (mixed), "
-                                     "1.4e-5 (fp16x2); bar 1e-3 (profiles/parity_512_r01.json, tests/test_pipeline_gpu.py)",
+                           "parity": "decoded RGB vs fp32 CPU oracle at this exact workload and precision mode, bar 1e-3: "
+                                     "tests/test_pipeline_gpu.py::test_benched_mode_parity_at_baseline_size",
                            "parallelism": f"dp{world}"},
                 "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-                "image_gflop": IMAGE_GFLOP,
+                "configs": configs, "image_gflop": IMAGE_GFLOP,
                 "image_frac_of_flop_roofline": (IMAGE_GFLOP / 1e3) * B / (t_res / args.steps) / peaks["tflops"]}
         print(json.dumps(line))
     import torch.distributed as tdist
@@ -380,6 +508,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("DFU_PRECISION", "mixed"), choices=["mixed", "fp16x2", "fp16"])
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip BASELINE configs 3/4/5 (batch 8, VAE batch 32, 768x768 CFG); they only run at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -31,7 +31,6 @@ def npass_of(prec: int) -> int:
 # launch accounting (bench.py reports `gpu_launches`) and optional per-kernel CUDA-event profiling
 # ---------------------------------------------------------------------------------------------
 STATS = {"launches": 0}
-ABLATE = set()  # kernel classes whose launches are skipped (timing ablation in bench.py only; results are garbage)
 PROFILE = None  # when a dict: kernel name -> list of (start_event, end_event, algorithmic_flops, algorithmic_bytes)
 
 
@@ -52,29 +51,6 @@ class _Prof:
             self.e1.record()
             PROFILE.setdefault(self.name, []).append((self.e0, self.e1, self.flops, self.nbytes))
         return False
-
-
-class _AblatingLib:
-    """Proxy over the CDLL that turns the ablated entry points into no-ops (bench.py timing ablation only)."""
-
-    def __init__(self, real):
-        self._real = real
-
-    def __getattr__(self, name):
-        fn = getattr(self._real, name)
-        cls = {"dfu_gemm": "gemm", "dfu_attention": "attention", "dfu_groupnorm": "groupnorm",
-               "dfu_layernorm": "layernorm"}.get(name)
-        if cls is not None and cls in ABLATE:
-            return lambda *a: 0
-        return fn
-
-
-_real_lib = lib
-
-
-def lib():  # noqa: F811  (shadows the imported loader on purpose)
-    L = _real_lib()
-    return _AblatingLib(L) if ABLATE else L
 
 
 def _stream() -> int:

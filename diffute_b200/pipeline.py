@@ -34,6 +34,7 @@ class DiffUTEPipeline:
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
         self.glyph_encoder, self.glyph_processor = glyph_encoder, glyph_processor
         self.device = unet.device
+        self.fuse_scheduler_step = True  # False: always run scheduler.step() as its own kernel (tests, custom schedulers)
         self._graphs = {}
         self._rows_cache = {}
 
@@ -102,7 +103,8 @@ class DiffUTEPipeline:
     def _step_graph(self, B, h, w, fused: bool):
         """Capture (once per shape) one denoising step: UNet + fused DDIM update, reading t / coefficients from the
         device `state` row that the loop refreshes with one small copy per step."""
-        key = (B, h, w, fused)
+        # the glyph-context length is a kernel argument (Nk, K/V strides) baked into the captured step
+        key = (B, h, w, fused, self.unet.n_ctx, self.unet.ctx_batch)
         g = self._graphs.get(key)
         if g is not None and g[2] == self.unet.buffer_generation():
             return g
@@ -161,7 +163,8 @@ class DiffUTEPipeline:
         sf = float(self.vae.config["scaling_factor"])
         do_cfg = guidance_scale != 1.0 and negative_glyph_embeds is not None
         sched = self.scheduler
-        fused = isinstance(sched, DDIMScheduler) and eta == 0.0 and not sched.config["clip_sample"] and not do_cfg
+        fused = (self.fuse_scheduler_step and isinstance(sched, DDIMScheduler) and eta == 0.0
+                 and not sched.config["clip_sample"] and not do_cfg)
         UB = 2 * B if do_cfg else B
 
         # --- step-invariant work (once per request) -------------------------------------------------
@@ -200,7 +203,7 @@ class DiffUTEPipeline:
             for i in range(len(ts)):
                 state.copy_(rows[i])       # one small D2D copy: timestep + DDIM coefficients of this step
                 graph.replay()             # UNet + scheduler update, latents advanced in place
-            latents = lat_buf
+            latents = lat_buf.clone()  # the arena buffer is overwritten by the next call: hand out a copy
         else:
             eps_g = torch.empty((B, 4, h, w), device=dev) if do_cfg else None
             for i, t in enumerate(ts):

@@ -427,7 +427,8 @@ class UNet2DConditionModel:
         return out
 
     def _run(self, B, H, W):
-        key = (B, H, W)
+        # the glyph-context length and batch are kernel arguments (Nk, K/V row strides) baked into a captured graph
+        key = (B, H, W, self.n_ctx, self.ctx_batch)
         if not self.use_cuda_graph:
             return self._forward_impl(B, H, W)
         g = self._graphs.get(key)

@@ -45,6 +45,39 @@ def test_unet_step_parity(setup, precision, tol, graph):
     assert ((out.cpu() - ref).abs().max() / ref.abs().max()).item() < tol
 
 
+@pytest.mark.parametrize("precision,tol", [("fp16", 4e-3), ("fp16x2", 2e-4)])
+def test_unet_step_parity_at_baseline_size(setup, precision, tol):
+    """L=64 (512 px): the tilings bench.py runs — 64-wide / 2-row conv boxes, 160-tile stream-K attention, the level-0
+    split-K clusters — which the L<=32 cases never reach."""
+    from diffute_b200.unet import UNet2DConditionModel
+    sd, orc = setup
+    unet = UNet2DConditionModel(sd, precision=precision, use_cuda_graph=True)
+    sample, ehs = _inputs(1, 64, 21)
+    ref = orc(sample, 981, ehs).sample
+    for rep in range(2):
+        got = unet(sample.cuda(), 981, ehs.cuda()).sample.cpu()
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        print(f"unet parity {precision} B=1 L=64 rep={rep}: maxrel {err:.3e}")
+        assert err < tol, err
+
+
+def test_unet_context_length_change_recaptures_graph(setup):
+    """A captured step bakes the glyph-context length (Nk and the K/V row strides) into its kernel arguments: a call
+    with a shorter encoder_hidden_states must not replay the graph captured for the longer one."""
+    from diffute_b200.unet import UNet2DConditionModel
+    sd, orc = setup
+    unet = UNet2DConditionModel(sd, precision="fp16x2", use_cuda_graph=True)
+    g = torch.Generator().manual_seed(5)
+    sample = torch.randn((1, 9, 16, 16), generator=g)
+    for T in (577, 77, 577, 130):
+        ehs = torch.randn((1, T, 1024), generator=g)
+        ref = orc(sample, 500, ehs).sample
+        got = unet(sample.cuda(), 500, ehs.cuda()).sample.cpu()
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        print(f"unet ctx T={T}: maxrel {err:.3e}")
+        assert err < 2e-4, (T, err)
+
+
 def test_unet_rejects_bad_shapes(setup):
     from diffute_b200.unet import UNet2DConditionModel
     sd, _ = setup
