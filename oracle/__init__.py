@@ -14,7 +14,16 @@ and is not installable offline, so the algorithm is restated from its published
 architecture.  PARITY PINS: exact parameter totals
 (UNet 865,925,124; VAE 83,653,863) and six upstream scheduler known-answer
 constants (tests/test_oracle_*.py).  UNet/VAE *outputs* have no golden vectors
-in the reference (it has no tests at all): "parity unpinned" for those.
+in the reference (it has no tests at all): "parity unpinned" against the
+reference itself.  Independent evidence instead: tests/test_oracle_crosscheck.py
+checks this package primitive by primitive, block by block and end to end
+against tests/refmath.py, a second restatement written in a different form
+(numpy float64, flat functional walk, explicit im2col/softmax/normalisation);
+they agree to <= 5e-6 (fp32 vs fp64 noise).  The same file holds a test that
+activates when the real package is importable and compares against diffusers'
+own UNet2DConditionModel / AutoencoderKL / DDIMScheduler on the same weights:
+
+    python -m pytest tests/test_oracle_crosscheck.py -k real_diffusers
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.  The product (diffute_b200/) never does.
