@@ -41,12 +41,34 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     FLAGS = globals()["FLAGS"] + (["-DDFU_TRACE"] if trace else [])
     bdir = os.path.join(HERE, "build", "trace") if trace else os.path.join(HERE, "build")
     dig = _digest() + ("+trace" if trace else "")
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig
+
+    if not force and fresh():
         return LIB
     if not os.path.exists(NVCC):
         if os.path.exists(LIB):
-            return LIB  # GPU box without a changed tree: use the prebuilt library that travelled with the snapshot
+            # a box without nvcc can only use the library that travelled with the snapshot — say so loudly when the
+            # sources it was built from are not the sources in this tree
+            sys.stderr.write(f"diffute_b200: WARNING: {os.path.basename(LIB)} does not match the source digest and nvcc "
+                             f"is not available to rebuild it; running the STALE binary\n")
+            return LIB
         raise RuntimeError(f"nvcc not found and no prebuilt {os.path.basename(LIB)}")
+    # one builder at a time (every torchrun rank calls build()): the others wait for the lock, then find a fresh library
+    import fcntl
+    os.makedirs(bdir, exist_ok=True)
+    with open(os.path.join(bdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB
+            return _compile(LIB, STAMP, FLAGS, bdir, dig, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _compile(LIB, STAMP, FLAGS, bdir, dig, verbose):
     objs = []
     procs = []
     os.makedirs(bdir, exist_ok=True)

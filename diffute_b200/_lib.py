@@ -42,6 +42,14 @@ class Gemm(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src2", C.c_void_p), ("dst", C.c_void_p), ("plane_stride", C.c_int64),
+        ("rows", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32), ("mode", C.c_int32),
+        ("dst_row0", C.c_int32), ("dst_ld", C.c_int32), ("geglu", C.c_int32), ("planes", C.c_int32),
+    ]
+
+
 EPI_F32, EPI_F16, EPI_GEGLU = 0, 1, 2
 
 _lib = None
@@ -105,6 +113,7 @@ SIGNATURES = {
     "dfu_attention": (_i, [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _i, _i64,
                            _i, _vp, _sz, _vp]),
     "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _i64, _vp]),
+    "dfu_pack_weights": (_i, [_vp, _vp, _i, _i64, _vp]),
     "dfu_trace_set_gemm": (_i, [_vp]),
     "dfu_trace_set_attn": (_i, [_vp]),
     "dfu_trace_set_norm": (_i, [_vp]),

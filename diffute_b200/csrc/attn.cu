@@ -639,10 +639,8 @@ extern "C" int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane
     p.ws_ml = p.ws_o + slots * 128 * 64;
   }
   const size_t smem = static_cast<size_t>(planes) * (kTile * 3 + 2 * kRing * kKvTile) + 256;
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(ONCE_ATTN_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   DFU_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(p.G), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream_), mQ, mK, mV, p));
   if (pieces)

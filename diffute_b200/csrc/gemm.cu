@@ -864,10 +864,8 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   e.out_planes = d->out_planes > 0 ? d->out_planes : 1;
   e.out_plane_stride = d->out_plane_stride;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(ONCE_GEMM_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set = true;
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
   static const bool cluster_ok = !(getenv("DFU_SPLITK_CLUSTER") && getenv("DFU_SPLITK_CLUSTER")[0] == '0');

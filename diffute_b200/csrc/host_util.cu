@@ -77,13 +77,28 @@ int pdl_enabled() {
   return v;
 }
 
+// Per-DEVICE caches: one process may drive several GPUs (the header promises "re-entrant per stream"), and both the SM
+// count and cudaFuncSetAttribute are properties of the current device, not of the process.
+constexpr int kMaxDevices = 64;
+
 int num_sms() {
-  static int n = 0;
-  if (n > 0) return n;
+  static int n[kMaxDevices];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  return n;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  if (n[dev] > 0) return n[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  n[dev] = v;
+  return v;
+}
+
+bool first_use_on_device(int slot) {
+  static bool done[kOnceSlots][kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || slot < 0 || slot >= kOnceSlots) return true;
+  if (done[slot][dev]) return false;
+  done[slot][dev] = true;
+  return true;
 }
 
 }  // namespace dfu

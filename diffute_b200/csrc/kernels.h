@@ -34,7 +34,12 @@ const char* get_error();
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device)
+
+// true the first time it is called for (slot, current device): guards per-device one-time setup such as
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which a second device in the same process needs again
+enum : int { ONCE_GEMM_ATTR = 0, ONCE_ATTN_ATTR, ONCE_GEMV_ATTR, ONCE_CONV_OUT_ATTR, ONCE_GEMM2_ATTR, kOnceSlots = 8 };
+bool first_use_on_device(int slot);
 
 // 1 unless DFU_PDL=0: launch with the programmatic-stream-serialization attribute (kernels call pdl_wait()).
 int pdl_enabled();

@@ -481,10 +481,8 @@ int dfu_gemv(const float* x, int B, int K, int ldx, const float* W, const float*
   DFU_REQUIRE(K % 4 == 0, "gemv: K=%d", K);
   const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
   DFU_REQUIRE(smem <= 96 * 1024, "gemv: B*K too large");
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(ONCE_GEMV_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
   }
   int blocks = (N + 7) / 8;
   const int cap = (num_sms() > 0 ? num_sms() : 148) * 4;
@@ -532,10 +530,8 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   // staging the weights pays only when a CTA then walks many pixels (VAE maps); the 64x64 UNet output conv keeps
   // one warp per pixel reading the weights through L1 (measured 11 us vs 19 us with the 46 KB copy per CTA)
   const int w_in_smem = wbytes <= 200 * 1024 && npix >= 64LL * 8 * (num_sms() > 0 ? num_sms() : 148);
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(ONCE_CONV_OUT_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_small_out_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   // eight pixels per CTA pass; enough CTAs for every SM, few enough that the weight copy is amortised over many pixels
   const int sms = num_sms() > 0 ? num_sms() : 148;

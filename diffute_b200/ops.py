@@ -62,8 +62,89 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 # ---------------------------------------------------------------------------------------------
-# one-time weight packing (load time, not on the sampling path)
+# one-time weight packing (load time, not on the sampling path): a job list executed by ONE dfu_pack_weights launch
 # ---------------------------------------------------------------------------------------------
+class Packer:
+    """Collects pack jobs (diffusers state-dict tensor -> kernel layout) and runs them in one launch.
+
+    Layouts: conv [O, I, kh, kw] -> fp16 [planes*O, kh*kw*I] with k = tap*I + i (tap-major, channels innermost);
+    linear [N, K] -> fp16 [planes*N, K]; plane 0 = RN(x), plane 1 = RN(x - plane0); GEGLU projections interleave
+    value / gate rows in blocks of 16; `into=` stacks several tensors into one matrix (q|k|v, the 22 time_emb_proj)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.jobs, self.prefix, self.total, self._keep = [], [], 0, []
+
+    def _src(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()  # a copy engine transfer, not a kernel
+        self._keep.append(t)
+        return t
+
+    def _job(self, src, dst, rows, cin, taps, *, mode=0, row0=0, ld=None, geglu=False, planes=0, plane_stride=0,
+             src2=None):
+        j = _lib.PackJob()
+        j.src, j.src2, j.dst = src.data_ptr(), (None if src2 is None else src2.data_ptr()), dst.data_ptr()
+        j.plane_stride, j.rows, j.cin, j.taps, j.mode = plane_stride, rows, cin, taps, mode
+        j.dst_row0, j.dst_ld, j.geglu, j.planes = row0, (ld if ld is not None else cin * taps), int(geglu), planes
+        self.jobs.append(j)
+        self.prefix.append(self.total)
+        self.total += rows * cin * taps
+
+    def weight16(self, w: torch.Tensor, planes: int, geglu: bool = False, into: Optional[torch.Tensor] = None,
+                 row0: int = 0, total_rows: Optional[int] = None) -> torch.Tensor:
+        """conv [O,I,kh,kw] or linear [N,K] -> fp16 [planes*rows, K] (K-major, tap-major).  `into` / `row0` /
+        `total_rows` stack several sources into one packed matrix of `total_rows` rows per plane."""
+        rows, cin = w.shape[0], w.shape[1]
+        taps = w.numel() // (rows * cin)
+        K = cin * taps
+        tr = total_rows if total_rows is not None else rows
+        dst = into if into is not None else torch.empty((planes * tr, K), dtype=torch.float16, device=self.device)
+        self._job(self._src(w), dst, rows, cin, taps, row0=row0, ld=K, geglu=geglu, planes=planes, plane_stride=tr * K)
+        return dst
+
+    def f32(self, t: torch.Tensor, add: Optional[torch.Tensor] = None, geglu: bool = False,
+            into: Optional[torch.Tensor] = None, row0: int = 0) -> torch.Tensor:
+        """fp32 copy of a vector / matrix (optionally + `add`, GEGLU row interleave, stacked `into` a larger matrix)."""
+        rows = t.shape[0]
+        cin = t.numel() // rows
+        dst = into if into is not None else torch.empty(tuple(t.shape), dtype=torch.float32, device=self.device)
+        self._job(self._src(t), dst, rows, cin, 1, row0=row0, ld=cin, geglu=geglu, planes=0,
+                  src2=None if add is None else self._src(add))
+        return dst
+
+    def small_in(self, w: torch.Tensor) -> torch.Tensor:
+        """[Cout, Cin, k, k] -> fp32 [Cin*k*k, Cout] (consecutive output channels contiguous; dfu_conv_small_in)."""
+        O, I = w.shape[0], w.shape[1]
+        taps = w.numel() // (O * I)
+        dst = torch.empty((I * taps, O), dtype=torch.float32, device=self.device)
+        self._job(self._src(w), dst, O, I, taps, mode=1, ld=O)
+        return dst
+
+    def small_out(self, w: torch.Tensor) -> torch.Tensor:
+        """[Cout, Cin, k, k] -> fp32 [Cout, k*k, Cin] (dfu_conv_small_out)."""
+        O, I = w.shape[0], w.shape[1]
+        taps = w.numel() // (O * I)
+        dst = torch.empty((O, taps, I), dtype=torch.float32, device=self.device)
+        self._job(self._src(w), dst, O, I, taps, ld=I * taps)
+        return dst
+
+    def run(self):
+        if not self.jobs:
+            return
+        n = len(self.jobs)
+        arr = (_lib.PackJob * n)(*self.jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        jobs_dev = host.to(self.device)
+        prefix_dev = torch.tensor(self.prefix, dtype=torch.int64).to(self.device)
+        with _Prof("pack_weights", 1):
+            check(lib().dfu_pack_weights(jobs_dev.data_ptr(), prefix_dev.data_ptr(), n, self.total, _stream()),
+                  "dfu_pack_weights")
+        torch.cuda.current_stream().synchronize()  # the job table and the fp32 sources may be freed after this
+        self.jobs, self.prefix, self.total, self._keep = [], [], 0, []
+
+
+# torch statements of the same layouts, for single tensors (operands built by tests / scripts, and the layout tests that
+# check dfu_pack_weights against them).  Model loading goes through Packer.
 def split_f16(x: torch.Tensor, planes: int) -> torch.Tensor:
     """fp32 [...] -> fp16 [planes, ...]: plane 0 = RN(x), plane 1 = RN(x - plane0)."""
     hi = x.to(torch.float16)
@@ -80,6 +161,13 @@ def pack_linear_weight(w: torch.Tensor, planes: int, geglu: bool = False) -> tor
     return split_f16(w.contiguous(), planes).reshape(planes * w.shape[0], w.shape[1])
 
 
+def pack_conv_weight(w: torch.Tensor, planes: int) -> torch.Tensor:
+    """[O, I, kh, kw] fp32 -> fp16 [planes*O, kh*kw*I] with k = tap*I + i (tap-major, channels innermost)."""
+    O, I, kh, kw = w.shape
+    wk = w.permute(0, 2, 3, 1).reshape(O, kh * kw * I)
+    return split_f16(wk.contiguous(), planes).reshape(planes * O, kh * kw * I)
+
+
 def geglu_interleave(w: torch.Tensor) -> torch.Tensor:
     """rows [a_0..a_{n-1}, g_0..g_{n-1}] -> blocks of 32 rows: 16 value rows then the matching 16 gate rows."""
     n2 = w.shape[0]
@@ -89,13 +177,6 @@ def geglu_interleave(w: torch.Tensor) -> torch.Tensor:
     a = a.reshape(n // 16, 16, *rest)
     g = g.reshape(n // 16, 16, *rest)
     return torch.cat([a, g], dim=1).reshape(n2, *rest).contiguous()
-
-
-def pack_conv_weight(w: torch.Tensor, planes: int) -> torch.Tensor:
-    """[O, I, kh, kw] fp32 -> fp16 [planes*O, kh*kw*I] with k = tap*I + i (tap-major, channels innermost)."""
-    O, I, kh, kw = w.shape
-    wk = w.permute(0, 2, 3, 1).reshape(O, kh * kw * I)
-    return split_f16(wk.contiguous(), planes).reshape(planes * O, kh * kw * I)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -79,6 +79,11 @@ class UNet2DConditionModel:
         cfg = dict(arch.SD2_INPAINT_UNET_CONFIG)
         if config:
             cfg.update({k: v for k, v in config.items() if not k.startswith("_")})
+        boc = list(cfg["block_out_channels"])
+        if isinstance(cfg["attention_head_dim"], int):  # diffusers accepts one int for all blocks
+            cfg["attention_head_dim"] = (cfg["attention_head_dim"],) * len(boc)
+        if len(cfg["attention_head_dim"]) != len(boc):
+            raise ValueError("attention_head_dim must be an int or one entry per block")
         self.config = _Config(cfg)
         self.device = torch.device(device)
         self.prec = _prec(precision)
@@ -93,11 +98,17 @@ class UNet2DConditionModel:
             if tuple(state_dict[k].shape) != tuple(s):
                 raise ValueError(f"{k}: expected shape {s}, got {tuple(state_dict[k].shape)}")
         self.layout = arch.unet_layout(cfg)
+        for blk in self.layout["down"] + [dict(self.layout["mid"], cout=self.layout["mid"]["ch"], attn=True)]:
+            if blk.get("attn") and blk["cout"] != 64 * blk["heads"]:
+                raise ValueError(f"attention head dim must be 64 (the fused attention kernel's tile): got {blk['cout']} "
+                                 f"channels over {blk['heads']} heads; attention_head_dim holds head COUNTS per block")
         self.ws = ops.Workspace(256 << 20, self.device)
         self.arena = Arena(self.device)
         self._graphs = {}
         self._ctx_key = None
-        self._pack(state_dict)
+        self._weights_generation = 0
+        self._sd = {k: state_dict[k].detach().to(torch.float32) for k in shapes}
+        self._pack(self._sd)
 
     # ------------------------------------------------------------------------------------------
     # loading
@@ -113,96 +124,155 @@ class UNet2DConditionModel:
         from . import synthetic
         return cls(synthetic.make_state_dict(arch.unet_param_shapes(), seed), **kw)
 
-    def _dev(self, t: torch.Tensor) -> torch.Tensor:
-        return t.to(device=self.device, dtype=torch.float32).contiguous()
-
     def _pack(self, sd):
+        """diffusers state dict -> kernel layouts, ONE dfu_pack_weights launch for the whole network."""
         P = self.planes
-        d = self._dev
+        pk = ops.Packer(self.device)
         w: Dict[str, torch.Tensor] = {}
         self.w = w
 
         def conv3(k):
-            w[k + ".w16"] = ops.pack_conv_weight(d(sd[k + ".weight"]), P)
-            w[k + ".b"] = d(sd[k + ".bias"])
+            w[k + ".w16"] = pk.weight16(sd[k + ".weight"], P)
+            w[k + ".b"] = pk.f32(sd[k + ".bias"])
 
         def lin(k, bias=True):
-            w[k + ".w16"] = ops.pack_linear_weight(d(sd[k + ".weight"]), P)
+            w[k + ".w16"] = pk.weight16(sd[k + ".weight"], P)
             if bias:
-                w[k + ".b"] = d(sd[k + ".bias"])
+                w[k + ".b"] = pk.f32(sd[k + ".bias"])
 
         def norm(k):
-            w[k + ".g"] = d(sd[k + ".weight"])
-            w[k + ".be"] = d(sd[k + ".bias"])
+            w[k + ".g"] = pk.f32(sd[k + ".weight"])
+            w[k + ".be"] = pk.f32(sd[k + ".bias"])
 
-        temb_w, temb_b, self.temb_off = [], [], {}
-        off = 0
+        def stacked(keys):
+            """several [n_i, K] linears stacked along N into one packed matrix (fused q|k|v / k|v projections)"""
+            rows = sum(sd[k].shape[0] for k in keys)
+            K = sd[keys[0]].shape[1]
+            dst = torch.empty((P * rows, K), dtype=torch.float16, device=self.device)
+            r0 = 0
+            for k in keys:
+                pk.weight16(sd[k], P, into=dst, row0=r0, total_rows=rows)
+                r0 += sd[k].shape[0]
+            return dst
 
-        def resnet(k):
-            nonlocal off
+        lay = self.layout
+        res_keys, tr_keys, conv_keys = [], [], []
+        self.attn_layers = []
+        for i, blk in enumerate(lay["down"]):
+            for j in range(blk["layers"]):
+                res_keys.append(f"down_blocks.{i}.resnets.{j}")
+                if blk["attn"]:
+                    tr_keys.append(f"down_blocks.{i}.attentions.{j}")
+                    self.attn_layers.append((tr_keys[-1], blk["cout"]))
+            if blk["down"]:
+                conv_keys.append(f"down_blocks.{i}.downsamplers.0.conv")
+        res_keys.append("mid_block.resnets.0")
+        tr_keys.append("mid_block.attentions.0")
+        self.attn_layers.append(("mid_block.attentions.0", lay["mid"]["ch"]))
+        res_keys.append("mid_block.resnets.1")
+        for i, blk in enumerate(lay["up"]):
+            for j in range(len(blk["skips"])):
+                res_keys.append(f"up_blocks.{i}.resnets.{j}")
+                if blk["attn"]:
+                    tr_keys.append(f"up_blocks.{i}.attentions.{j}")
+                    self.attn_layers.append((tr_keys[-1], blk["cout"]))
+            if blk["up"]:
+                conv_keys.append(f"up_blocks.{i}.upsamplers.0.conv")
+
+        # the 22 time_emb_proj layers are stacked into one [sum(Cout), 1280] fp32 matrix (one GEMV per step)
+        self.temb_off, off = {}, 0
+        for k in res_keys:
+            self.temb_off[k] = off
+            off += sd[k + ".time_emb_proj.weight"].shape[0]
+        self.temb_total = off
+        tdim = sd[res_keys[0] + ".time_emb_proj.weight"].shape[1]
+        w["temb_proj.w"] = torch.empty((off, tdim), dtype=torch.float32, device=self.device)
+        w["temb_proj.b"] = torch.empty((off,), dtype=torch.float32, device=self.device)
+        for k in res_keys:
             norm(k + ".norm1")
             conv3(k + ".conv1")
             norm(k + ".norm2")
-            conv3(k + ".conv2")
-            temb_w.append(d(sd[k + ".time_emb_proj.weight"]))
-            temb_b.append(d(sd[k + ".time_emb_proj.bias"]))
-            self.temb_off[k] = off
-            off += temb_w[-1].shape[0]
-            if k + ".conv_shortcut.weight" in sd:
-                w[k + ".sc.w16"] = ops.pack_conv_weight(d(sd[k + ".conv_shortcut.weight"]), P)
-                w[k + ".conv2.b"] = w[k + ".conv2.b"] + d(sd[k + ".conv_shortcut.bias"])
-
-        def transformer(k):
+            w[k + ".conv2.w16"] = pk.weight16(sd[k + ".conv2.weight"], P)
+            if k + ".conv_shortcut.weight" in sd:  # fused 1x1 shortcut: second operand group, bias folded into conv2's
+                w[k + ".sc.w16"] = pk.weight16(sd[k + ".conv_shortcut.weight"], P)
+                w[k + ".conv2.b"] = pk.f32(sd[k + ".conv2.bias"], add=sd[k + ".conv_shortcut.bias"])
+            else:
+                w[k + ".conv2.b"] = pk.f32(sd[k + ".conv2.bias"])
+            pk.f32(sd[k + ".time_emb_proj.weight"], into=w["temb_proj.w"], row0=self.temb_off[k])
+            pk.f32(sd[k + ".time_emb_proj.bias"].reshape(-1, 1), into=w["temb_proj.b"], row0=self.temb_off[k])
+        for k in tr_keys:
             norm(k + ".norm")
             lin(k + ".proj_in")
             lin(k + ".proj_out")
             b = k + ".transformer_blocks.0"
             for n in ("norm1", "norm2", "norm3"):
                 norm(f"{b}.{n}")
-            qkv = torch.cat([d(sd[f"{b}.attn1.to_{x}.weight"]) for x in "qkv"], 0)
-            w[b + ".attn1.qkv.w16"] = ops.pack_linear_weight(qkv, P)
+            w[b + ".attn1.qkv.w16"] = stacked([f"{b}.attn1.to_{x}.weight" for x in "qkv"])
             lin(b + ".attn1.to_out.0")
             lin(b + ".attn2.to_q", bias=False)
-            kv = torch.cat([d(sd[f"{b}.attn2.to_{x}.weight"]) for x in "kv"], 0)
-            w[b + ".attn2.kv.w16"] = ops.pack_linear_weight(kv, P)
+            w[b + ".attn2.kv.w16"] = stacked([f"{b}.attn2.to_{x}.weight" for x in "kv"])
             lin(b + ".attn2.to_out.0")
-            w[b + ".ff.net.0.proj.w16"] = ops.pack_linear_weight(d(sd[b + ".ff.net.0.proj.weight"]), P, geglu=True)
-            w[b + ".ff.net.0.proj.b"] = ops.geglu_interleave(d(sd[b + ".ff.net.0.proj.bias"]))
+            w[b + ".ff.net.0.proj.w16"] = pk.weight16(sd[b + ".ff.net.0.proj.weight"], P, geglu=True)
+            w[b + ".ff.net.0.proj.b"] = pk.f32(sd[b + ".ff.net.0.proj.bias"].reshape(-1, 1), geglu=True).reshape(-1)
             lin(b + ".ff.net.2")
-
-        self.attn_layers = []
-        w["conv_in.w"] = ops.pack_small_in_weight(d(sd["conv_in.weight"]))
-        w["conv_in.b"] = d(sd["conv_in.bias"])
+        for k in conv_keys:
+            conv3(k)
+        w["conv_in.w"] = pk.small_in(sd["conv_in.weight"])
+        w["conv_in.b"] = pk.f32(sd["conv_in.bias"])
         for n in ("time_embedding.linear_1", "time_embedding.linear_2"):
-            w[n + ".w"] = d(sd[n + ".weight"])
-            w[n + ".b"] = d(sd[n + ".bias"])
-        lay = self.layout
-        for i, blk in enumerate(lay["down"]):
-            for j in range(blk["layers"]):
-                resnet(f"down_blocks.{i}.resnets.{j}")
-                if blk["attn"]:
-                    transformer(f"down_blocks.{i}.attentions.{j}")
-                    self.attn_layers.append((f"down_blocks.{i}.attentions.{j}", blk["cout"]))
-            if blk["down"]:
-                conv3(f"down_blocks.{i}.downsamplers.0.conv")
-        resnet("mid_block.resnets.0")
-        transformer("mid_block.attentions.0")
-        self.attn_layers.append(("mid_block.attentions.0", lay["mid"]["ch"]))
-        resnet("mid_block.resnets.1")
-        for i, blk in enumerate(lay["up"]):
-            for j in range(len(blk["skips"])):
-                resnet(f"up_blocks.{i}.resnets.{j}")
-                if blk["attn"]:
-                    transformer(f"up_blocks.{i}.attentions.{j}")
-                    self.attn_layers.append((f"up_blocks.{i}.attentions.{j}", blk["cout"]))
-            if blk["up"]:
-                conv3(f"up_blocks.{i}.upsamplers.0.conv")
+            w[n + ".w"] = pk.f32(sd[n + ".weight"])
+            w[n + ".b"] = pk.f32(sd[n + ".bias"])
         norm("conv_norm_out")
-        w["conv_out.wp"] = ops.pack_small_out_weight(d(sd["conv_out.weight"]))
-        w["conv_out.b"] = d(sd["conv_out.bias"])
-        w["temb_proj.w"] = torch.cat(temb_w, 0).contiguous()
-        w["temb_proj.b"] = torch.cat(temb_b, 0).contiguous()
-        self.temb_total = off
+        w["conv_out.wp"] = pk.small_out(sd["conv_out.weight"])
+        w["conv_out.b"] = pk.f32(sd["conv_out.bias"])
+        pk.run()
+
+    # ------------------------------------------------------------------------------------------
+    # nn.Module surface the reference's training / checkpoint hooks touch (train_diffute_v1.py:664-687)
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """diffusers key -> fp32 tensor (the tensors this model was loaded from, in inventory order)."""
+        return {k: self._sd[k] for k in arch.unet_param_shapes(self.config)}
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        shapes = arch.unet_param_shapes(self.config)
+        missing = [k for k in shapes if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in shapes]
+        if missing or (strict and unexpected):
+            raise KeyError(f"UNet state dict: {len(missing)} missing keys (e.g. {missing[:3]}), "
+                           f"{len(unexpected)} unexpected (e.g. {unexpected[:3]})")
+        for k, s in shapes.items():
+            if tuple(state_dict[k].shape) != tuple(s):
+                raise ValueError(f"{k}: expected shape {s}, got {tuple(state_dict[k].shape)}")
+        self._sd = {k: state_dict[k].detach().to(torch.float32) for k in shapes}
+        self._pack(self._sd)
+        self._graphs.clear()          # captured steps hold the old packed-weight addresses
+        self._weights_generation += 1
+        self._ctx_key = None
+        return self
+
+    def parameters(self):
+        return iter(self.state_dict().values())
+
+    def named_parameters(self):
+        return iter(self.state_dict().items())
+
+    def register_to_config(self, **kwargs):
+        """diffusers ConfigMixin.register_to_config (train_diffute_v1.py:687 copies a loaded model's config over).
+        Architecture-defining entries may not change under a loaded model."""
+        new = dict(self.config)
+        new.update({k: v for k, v in kwargs.items() if not k.startswith("_")})
+        if dict(arch.unet_param_shapes(new)) != dict(arch.unet_param_shapes(self.config)):
+            raise ValueError("register_to_config: the new config describes a different architecture than the loaded "
+                             "weights; build a new UNet2DConditionModel instead")
+        self.config = _Config(new)
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True, **kw):
+        """Writes `<save_directory>/config.json` + `diffusion_pytorch_model.{safetensors|bin}` — the layout
+        `from_pretrained(parent, subfolder=basename)` reads back (train_diffute_v1.py:669 saves to `<out>/unet`)."""
+        from .checkpoint import save_diffusers_folder
+        save_diffusers_folder(save_directory, None, dict(self.config), self.state_dict(), "UNet2DConditionModel",
+                              safe_serialization=safe_serialization)
 
     # nn.Module-ish conveniences the reference scripts touch (train_diffute_v1.py:657, :696, :859)
     def eval(self):
@@ -445,7 +515,7 @@ class UNet2DConditionModel:
         return g[1]
 
     def buffer_generation(self):
-        return (self.arena.generation, self.ws.generation)
+        return (self.arena.generation, self.ws.generation, self._weights_generation)
 
     @torch.no_grad()
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None,

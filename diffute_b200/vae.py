@@ -110,7 +110,8 @@ class AutoencoderKL:
                 raise ValueError(f"{k}: expected shape {s}, got {tuple(t.shape)}")
         self.arena = Arena(self.device)
         self.ws = ops.Workspace(256 << 20, self.device)
-        self._pack(sd)
+        self._sd = {k: sd[k].detach().to(torch.float32) for k in shapes}
+        self._pack(self._sd)
 
     @classmethod
     def from_pretrained(cls, path, subfolder: Optional[str] = "vae", revision=None, **kw):
@@ -146,31 +147,51 @@ class AutoencoderKL:
         return ops.planes_of(self.enc_prec if enc else self.dec_prec)
 
     def _pack(self, sd):
+        """diffusers state dict -> kernel layouts, ONE dfu_pack_weights launch (see ops.Packer)."""
         w: Dict[str, torch.Tensor] = {}
         self.w = w
-        d = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        pk = ops.Packer(self.device)
         for k, t in sd.items():
             P = self._planes_for(k)
             if k.endswith(".weight") and t.dim() == 4 and t.shape[0] > 8 and t.shape[1] > 16:
-                w[k[:-7] + ".w16"] = ops.pack_conv_weight(d(t), P)     # tensor-core convs
+                w[k[:-7] + ".w16"] = pk.weight16(t, P)     # tensor-core convs
             elif k.endswith(".weight") and t.dim() == 2:
-                w[k[:-7] + ".w16"] = ops.pack_linear_weight(d(t), P)   # attention projections
-            w[k] = d(t)
+                w[k[:-7] + ".w16"] = pk.weight16(t, P)     # attention projections
+            elif t.dim() == 1:
+                w[k] = pk.f32(t)                            # biases, GroupNorm affine parameters
         # fused 1x1 shortcut bias folds into conv2's bias
-        for k in list(sd.keys()):
+        for k in sd:
             if k.endswith(".conv_shortcut.bias"):
                 base = k[: -len(".conv_shortcut.bias")]
-                w[base + ".conv2.bias_sc"] = w[base + ".conv2.bias"] + w[k]
+                w[base + ".conv2.bias_sc"] = pk.f32(sd[base + ".conv2.bias"], add=sd[k])
         for side in ("encoder", "decoder"):
             a = f"{side}.mid_block.attentions.0"
-            qkv = torch.cat([sd[f"{a}.to_{x}.weight"] for x in "qkv"], 0)
-            w[a + ".qkv.w16"] = ops.pack_linear_weight(d(qkv), self._planes_for(a))
-            w[a + ".qkv.b"] = torch.cat([d(sd[f"{a}.to_{x}.bias"]) for x in "qkv"], 0)
-        w["encoder.conv_out.wp"] = ops.pack_small_out_weight(w["encoder.conv_out.weight"])
-        w["decoder.conv_out.wp"] = ops.pack_small_out_weight(w["decoder.conv_out.weight"])
+            P = self._planes_for(a)
+            C = sd[f"{a}.to_q.weight"].shape[0]
+            w[a + ".qkv.w16"] = torch.empty((P * 3 * C, C), dtype=torch.float16, device=self.device)
+            w[a + ".qkv.b"] = torch.empty((3 * C,), dtype=torch.float32, device=self.device)
+            for i, x in enumerate("qkv"):
+                pk.weight16(sd[f"{a}.to_{x}.weight"], P, into=w[a + ".qkv.w16"], row0=i * C, total_rows=3 * C)
+                pk.f32(sd[f"{a}.to_{x}.bias"].reshape(-1, 1), into=w[a + ".qkv.b"], row0=i * C)
+        w["encoder.conv_out.wp"] = pk.small_out(sd["encoder.conv_out.weight"])
+        w["decoder.conv_out.wp"] = pk.small_out(sd["decoder.conv_out.weight"])
         for k in ("encoder.conv_in", "post_quant_conv", "decoder.conv_in"):
-            w[k + ".wt"] = ops.pack_small_in_weight(w[k + ".weight"])
-        w["quant_conv.w2"] = w["quant_conv.weight"].reshape(w["quant_conv.weight"].shape[0], -1).contiguous()
+            w[k + ".wt"] = pk.small_in(sd[k + ".weight"])
+        qw = sd["quant_conv.weight"]
+        w["quant_conv.w2"] = pk.f32(qw.reshape(qw.shape[0], -1))
+        pk.run()
+
+    # nn.Module surface (train_vae.py / train_diffute_v1.py touch these on the frozen VAE)
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: self._sd[k] for k in arch.vae_param_shapes(self.config)}
+
+    def parameters(self):
+        return iter(self.state_dict().values())
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True, **kw):
+        from .checkpoint import save_diffusers_folder
+        save_diffusers_folder(save_directory, None, dict(self.config), self.state_dict(), "AutoencoderKL",
+                              safe_serialization=safe_serialization)
 
     # ------------------------------------------------------------------------------------------
     def _op16(self, name, shape):

@@ -199,6 +199,30 @@ int dfu_attention(const void* q, int ldq, int q_col0, int64_t q_plane_stride, co
                   int planes, float scale, void* out, int ldo, int64_t out_plane_stride, int kv_splits,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- load-time weight packing --------------------------------------------------------------------
+ * One launch repacks a whole list of parameters from the diffusers state-dict layout (what
+ * UNet2DConditionModel.from_pretrained / AutoencoderKL.from_pretrained read, app.ipynb:550-553) into the kernels'
+ * layouts.  Job j covers rows*taps*cin elements; prefix[j] = elements of jobs 0..j-1 (device, int64).
+ *   src  fp32 [rows][cin][taps]  (torch [Cout, Cin, kh, kw] flattened; taps = 1 for linear / vectors)
+ *   mode 0: dst[(dst_row0 + r') * dst_ld + tap*cin + ci]  — K-major, tap-major; r' = r, or the GEGLU interleave
+ *           (blocks of 16 value rows / 16 gate rows) when geglu = 1; planes 0 -> fp32, 1 -> fp16, 2 -> fp16 hi + lo
+ *           (lo at + plane_stride elements);
+ *   mode 1: fp32 transposed dst[(ci*taps + tap) * dst_ld + dst_row0 + r]  (dfu_conv_small_in weights).
+ *   src2 (optional) is added elementwise before packing (conv2 bias + folded conv_shortcut bias). */
+typedef struct DfuPackJob {
+  const float* src;
+  const float* src2;
+  void* dst;
+  int64_t plane_stride;
+  int32_t rows, cin, taps;
+  int32_t mode;
+  int32_t dst_row0, dst_ld;
+  int32_t geglu;
+  int32_t planes;
+} DfuPackJob;
+int dfu_pack_weights(const DfuPackJob* jobs_dev, const int64_t* prefix_dev, int njobs, int64_t total_elements,
+                     void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * In-kernel timeline records (one per CTA: grid id, kernel tag, SM, globaltimer / clock64 phase stamps) for
  * scripts/trace_step.py.  `buf` = device u64 array: [0] next record (zeroed by the caller), [1] capacity in records,

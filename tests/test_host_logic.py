@@ -55,6 +55,13 @@ def test_struct_layout_matches_header(tmp_path):
     want = [C.sizeof(_lib.GemmOperand), C.sizeof(_lib.Gemm), _lib.GemmOperand.b.offset, _lib.GemmOperand.tap_dn.offset,
             _lib.Gemm.g.offset, _lib.Gemm.conv.offset, _lib.Gemm.sync_words.offset]
     assert got == want, (got, want)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "diffute_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu\\n", sizeof(DfuPackJob), offsetof(DfuPackJob,dst), '
+                   'offsetof(DfuPackJob,rows), offsetof(DfuPackJob,planes));return 0;}')
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(_lib.PackJob), _lib.PackJob.dst.offset, _lib.PackJob.rows.offset, _lib.PackJob.planes.offset]
+    assert got == want, (got, want)
 
 
 def test_weight_packing_and_geglu_interleave():

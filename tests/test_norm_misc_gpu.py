@@ -172,3 +172,38 @@ def test_groupnorm_two_launch_path_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "test_groupnorm and not subprocess"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_pack_weights_kernel_matches_torch_layouts():
+    """dfu_pack_weights (one launch for a whole job list) against the torch statements of every layout it produces."""
+    from diffute_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s: torch.randn(s, generator=g)
+    wc, wl, wg, bg = r(96, 64, 3, 3), r(128, 192), r(256, 64), r(256)
+    q, k, v = r(64, 128), r(64, 128), r(64, 128)
+    b1, b2, wi, wo = r(96), r(96), r(320, 9, 3, 3), r(4, 320, 3, 3)
+    for planes in (1, 2):
+        pk = ops.Packer("cuda")
+        c16 = pk.weight16(wc, planes)
+        l16 = pk.weight16(wl, planes)
+        g16 = pk.weight16(wg, planes, geglu=True)
+        gb = pk.f32(bg.reshape(-1, 1), geglu=True).reshape(-1)
+        qkv = torch.empty((planes * 192, 128), dtype=torch.float16, device="cuda")
+        for i, t in enumerate((q, k, v)):
+            pk.weight16(t, planes, into=qkv, row0=64 * i, total_rows=192)
+        bsum = pk.f32(b1, add=b2)
+        si, so = pk.small_in(wi), pk.small_out(wo)
+        stack = torch.empty((192, 128), dtype=torch.float32, device="cuda")
+        pk.f32(q, into=stack, row0=0)
+        pk.f32(k, into=stack, row0=64)
+        pk.f32(v, into=stack, row0=128)
+        pk.run()
+        assert torch.equal(c16.cpu(), ops.pack_conv_weight(wc, planes))
+        assert torch.equal(l16.cpu(), ops.pack_linear_weight(wl, planes))
+        assert torch.equal(g16.cpu(), ops.pack_linear_weight(wg, planes, geglu=True))
+        assert torch.equal(gb.cpu(), ops.geglu_interleave(bg))
+        assert torch.equal(qkv.cpu(), ops.pack_linear_weight(torch.cat([q, k, v], 0), planes))
+        assert torch.equal(bsum.cpu(), b1 + b2)
+        assert torch.equal(si.cpu(), ops.pack_small_in_weight(wi))
+        assert torch.equal(so.cpu(), ops.pack_small_out_weight(wo))
+        assert torch.equal(stack.cpu(), torch.cat([q, k, v], 0))

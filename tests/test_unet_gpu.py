@@ -78,6 +78,44 @@ def test_unet_context_length_change_recaptures_graph(setup):
         assert err < 2e-4, (T, err)
 
 
+@pytest.mark.parametrize("safe", [True, False])
+def test_unet_checkpoint_folder_round_trip(setup, tmp_path, safe):
+    """f1: the on-disk format the reference writes with `unet.save_pretrained(<out>/unet)` (train_diffute_v1.py:669)
+    and reads with `UNet2DConditionModel.from_pretrained(path, subfolder="unet")` (app.ipynb:551-553,
+    train_diffute_v1.py:684), as .safetensors and as .bin; plus the nn.Module surface of the load hook
+    (`register_to_config(**loaded.config)`, `load_state_dict(loaded.state_dict())`, train_diffute_v1.py:687-689)."""
+    import os
+    from diffute_b200.unet import UNet2DConditionModel
+    sd, orc = setup
+    a = UNet2DConditionModel(sd, precision="fp16x2")
+    a.save_pretrained(os.path.join(tmp_path, "unet"), safe_serialization=safe)
+    assert os.path.isfile(tmp_path / "unet" / ("diffusion_pytorch_model.safetensors" if safe else "diffusion_pytorch_model.bin"))
+    b = UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet", precision="fp16x2")
+    assert b.config.cross_attention_dim == 1024 and list(b.config.block_out_channels) == [320, 640, 1280, 1280]
+    got_sd = b.state_dict()
+    assert list(got_sd) == list(sd) and all(torch.equal(got_sd[k].cpu(), sd[k]) for k in sd)
+    assert sum(p.numel() for p in b.parameters()) == 865_925_124
+    sample, ehs = _inputs(1, 16, 31)
+    ref = orc(sample, 500, ehs).sample
+    err = ((b(sample.cuda(), 500, ehs.cuda()).sample.cpu() - ref).abs().max() / ref.abs().max()).item()
+    print(f"from_pretrained(safe={safe}) vs oracle: maxrel {err:.3e}")
+    assert err < 2e-4
+    if safe:
+        # the accelerate load hook: copy config + weights of a freshly loaded model into a live one
+        sd2 = {k: (v * 1.5 if k.endswith("conv_out.weight") else v) for k, v in sd.items()}
+        c = UNet2DConditionModel(sd2, precision="fp16x2")
+        out_before = c(sample.cuda(), 500, ehs.cuda()).sample.cpu()
+        assert ((out_before - ref).abs().max() / ref.abs().max()).item() > 1e-2
+        c.register_to_config(**b.config)
+        c.load_state_dict(b.state_dict())
+        err = ((c(sample.cuda(), 500, ehs.cuda()).sample.cpu() - ref).abs().max() / ref.abs().max()).item()
+        assert err < 2e-4, err
+        with pytest.raises(ValueError):
+            c.register_to_config(cross_attention_dim=768)
+        with pytest.raises(KeyError):
+            c.load_state_dict({k: v for k, v in sd.items() if k != "conv_in.bias"})
+
+
 def test_unet_rejects_bad_shapes(setup):
     from diffute_b200.unet import UNet2DConditionModel
     sd, _ = setup
