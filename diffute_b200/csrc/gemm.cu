@@ -13,134 +13,10 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
-#include "kernels.h"
+#include "gemm_shared.cuh"
 
 namespace dfu {
 
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
-constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
-constexpr int kEpiThreads = 256;
-constexpr int kMaxStages = 12;
-constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KiB smem slot for A (box may fill fewer rows)
-
-struct GroupDev {
-  int a_mode, ntaps, nchunks, a_plane, b_plane, kb_per_pass;
-  int b_static;  // B of this group is a constant (weights): may be fetched before the producer kernel completes
-  int8_t dn[9], dy[9], dx[9];
-};
-
-struct EpiParams {
-  int M, N;
-  int epi;
-  float alpha;
-  const float* bias;
-  const float* rowvec;
-  int rowvec_ld, rows_per_sample;
-  const float* residual;
-  int ldr;
-  float* out_f32;
-  int ldo;
-  __half* out_f16;
-  int ldh;
-  int out_planes;
-  long long out_plane_stride;
-};
-
-struct GemmKernelParams {
-  int block_n, tiles_m, tiles_n, splits, stages, total_kb;
-  int ngroups, npass;
-  GroupDev g[2];
-  int conv, B, H, W, bw, bh, bn, tiles_x, tiles_y;
-  uint32_t a_tx_bytes[2];  // bytes one A box delivers (per group)
-  uint32_t b_tx_bytes;
-  uint32_t tmem_cols;
-  float* ws;
-  int cluster;         // > 1: the `splits` K-slices of a tile form a thread-block cluster and reduce through DSMEM
-  unsigned int* sync;  // grid-barrier words (zero between launches); non-null => fused split-K second stage
-  EpiParams e;
-};
-
-// ---------------------------------------------------------------------------------------------
-// shared epilogue, one 4-column quad of output row m at a time so that consecutive lanes touch consecutive 16-byte
-// pieces of a row (coalesced residual loads and output stores).
-//   v = alpha*acc + bias[n] + rowvec[sample(m), n] + residual[m, n]  ->  fp32 | fp16 hi/lo planes
-//   GEGLU: out[m, n/2] = (a + bias_a) * gelu_erf(g + bias_g), a/g = value / gate quads 16 columns apart
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_f16x4(__half* dst, float4 v, bool lo_plane, long long plane_stride) {
-  __align__(8) __half h[4];
-  h[0] = __float2half_rn(v.x); h[1] = __float2half_rn(v.y); h[2] = __float2half_rn(v.z); h[3] = __float2half_rn(v.w);
-  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
-  if (lo_plane) {
-    __align__(8) __half l[4];
-    l[0] = __float2half_rn(v.x - __half2float(h[0]));
-    l[1] = __float2half_rn(v.y - __half2float(h[1]));
-    l[2] = __float2half_rn(v.z - __half2float(h[2]));
-    l[3] = __float2half_rn(v.w - __half2float(h[3]));
-    *reinterpret_cast<uint2*>(dst + plane_stride) = *reinterpret_cast<const uint2*>(l);
-  }
-}
-
-// (the epilogue is instruction-issue bound — ~2000 cycles per 32-column chunk round at 16 epilogue warps per SM, measured
-// with scripts/trace_step.py — so everything per-row is hoisted by the callers and alpha == 1 costs nothing)
-__device__ __forceinline__ float4 epi_affine(const EpiParams& e, int m, int n, float4 v, const float* sbias = nullptr,
-                                             int n_tile0 = 0) {
-  if (e.alpha != 1.0f) {
-    v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
-  }
-  if (e.bias) {
-    const float4 t = sbias ? *reinterpret_cast<const float4*>(sbias + (n - n_tile0))
-                           : __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  }
-  if (e.rowvec) {
-    // one sample per 128-row tile is the common case (rows_per_sample >= 128): the division is then a compare
-    const int smp = (m < e.rows_per_sample) ? 0 : m / e.rows_per_sample;
-    const float4 t = __ldg(reinterpret_cast<const float4*>(e.rowvec + static_cast<size_t>(smp) * e.rowvec_ld + n));
-    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  }
-  return v;
-}
-
-// residual already fetched by the caller (t = 0 when there is none)
-__device__ __forceinline__ void epi_quad_res(const EpiParams& e, int m, int n, float4 v, float4 t,
-                                             const float* sbias = nullptr, int n_tile0 = 0) {
-  v = epi_affine(e, m, n, v, sbias, n_tile0);
-  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  if (e.epi == DFU_EPI_F32) {
-    *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;
-  } else {
-    store_f16x4(e.out_f16 + static_cast<size_t>(m) * e.ldh + n, v, e.out_planes > 1, e.out_plane_stride);
-  }
-}
-
-__device__ __forceinline__ void epi_quad(const EpiParams& e, int m, int n, float4 v) {
-  v = epi_affine(e, m, n, v);
-  if (e.residual) {
-    const float4 t = *reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(m) * e.ldr + n);
-    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  }
-  if (e.epi == DFU_EPI_F32) {
-    *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;
-  } else {
-    store_f16x4(e.out_f16 + static_cast<size_t>(m) * e.ldh + n, v, e.out_planes > 1, e.out_plane_stride);
-  }
-}
-
-// n_a = packed column of the value quad (the gate quad sits at n_a + 16); output column = block*16 + offset
-__device__ __forceinline__ void epi_geglu_quad(const EpiParams& e, int m, int n_a, float4 a, float4 g,
-                                               const float* sbias = nullptr, int n_tile0 = 0) {
-  a = epi_affine(e, m, n_a, a, sbias, n_tile0);
-  g = epi_affine(e, m, n_a + 16, g, sbias, n_tile0);
-  float4 o;
-  o.x = a.x * gelu_erf_f(g.x); o.y = a.y * gelu_erf_f(g.y); o.z = a.z * gelu_erf_f(g.z); o.w = a.w * gelu_erf_f(g.w);
-  const int n_out = (n_a >> 5) * 16 + (n_a & 15);
-  store_f16x4(e.out_f16 + static_cast<size_t>(m) * e.ldh + n_out, o, e.out_planes > 1, e.out_plane_stride);
-}
-
-constexpr int kStageLd = 36;                          // floats per staged row (16-byte aligned, conflict-free)
-constexpr int kStageFloats = 32 * kStageLd;           // per epilogue warp
 
 // split-K second stage: every thread owns one output quad, sums the `splits` fp32 partials in slice order
 // (deterministic), four independent 16-byte loads in flight at a time, then runs the fused epilogue.
@@ -637,14 +513,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct Plan {
-  int block_n, splits, stages, tiles_m, tiles_n, total_kb;
-  int bw, bh, bn, tiles_x, tiles_y;
-  size_t ws_bytes;
-  size_t smem_bytes;
-};
+// shared memory of the pair kernel: ring + 8 x 4.5 KiB epilogue staging + alignment slack
+static size_t pair_smem(int stages, size_t stage_bytes) { return stages * stage_bytes + 8 * kStageFloats * 4 + 1024; }
 
-static int plan_gemm(const DfuGemm* d, Plan* pl) {
+int plan_gemm(const DfuGemm* d, Plan* pl) {
+  pl->pair = 0;
   DFU_REQUIRE(d->m > 0 && d->n > 0, "gemm: empty problem m=%d n=%d", d->m, d->n);
   DFU_REQUIRE(d->ngroups == 1 || d->ngroups == 2, "gemm: ngroups must be 1 or 2");
   DFU_REQUIRE(d->npass == 1 || d->npass == 3, "gemm: npass must be 1 or 3");
@@ -685,6 +558,43 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
     pl->tiles_m = (d->m + kBlockM - 1) / kBlockM;
   }
   const int sms = num_sms() > 0 ? num_sms() : 148;
+  DFU_REQUIRE(d->kernel >= 0 && d->kernel <= 2, "gemm: kernel=%d (0 auto, 1 tile-per-CTA, 2 persistent pairs)", d->kernel);
+  // ---- persistent CTA-pair kernel (gemm2.cu): explicit, or automatic when the 256-row pair tiles alone fill the GPU
+  {
+    int pbn = 0;
+    if (d->kernel == 2) {
+      pbn = d->block_n;
+      if (pbn <= 0) {
+        const int cands[] = {256, 192, 160, 128, 96, 80, 64, 32};
+        for (int c : cands)
+          if (d->n % c == 0 && (d->epi != DFU_EPI_GEGLU || c % 32 == 0)) { pbn = c; break; }
+      }
+      DFU_REQUIRE(d->splits <= 1, "gemm: the pair kernel has no split-K (splits=%d)", d->splits);
+    } else if (d->kernel == 0 && d->block_n <= 0 && d->splits <= 0) {
+      const int cands[] = {256, 192, 160, 128};
+      for (int c : cands)
+        if (d->n % c == 0 && (d->epi != DFU_EPI_GEGLU || c % 32 == 0)) { pbn = c; break; }
+      const long long pair_tiles = static_cast<long long>((pl->tiles_m + 1) / 2) * (pbn ? d->n / pbn : 0);
+      if (pair_tiles < (sms / 2) * 2 || total_kb < 4) pbn = 0;  // under two waves of pairs: the tile-per-CTA kernel
+    }
+    if (pbn > 0) {
+      DFU_REQUIRE(pbn % 16 == 0 && pbn >= 32 && pbn <= 256 && d->n % pbn == 0, "gemm: bad pair block_n=%d for n=%d", pbn, d->n);
+      DFU_REQUIRE(d->epi != DFU_EPI_GEGLU || pbn % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0, got %d", pbn);
+      pl->pair = 1;
+      pl->block_n = pbn;
+      pl->tiles_n = d->n / pbn;
+      pl->splits = 1;
+      pl->ws_bytes = 0;
+      const size_t stage_bytes = (d->npass == 3 ? 2 : 1) * (kABytes + static_cast<size_t>(pbn) * 64);
+      int stages = d->stages > 0 ? d->stages : kMaxStages;
+      if (stages > kMaxStages) stages = kMaxStages;
+      while (stages > 2 && pair_smem(stages, stage_bytes) > 226 * 1024) --stages;
+      pl->stages = stages;
+      pl->smem_bytes = pair_smem(stages, stage_bytes);
+      DFU_REQUIRE(pl->smem_bytes <= 226 * 1024, "gemm: pair smem %zu too large", pl->smem_bytes);
+      return DFU_OK;
+    }
+  }
   int bn_ = d->block_n;
   int splits = d->splits;
   if (bn_ <= 0 || splits <= 0) {
@@ -753,8 +663,8 @@ static int plan_gemm(const DfuGemm* d, Plan* pl) {
   return DFU_OK;
 }
 
-static int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& pl, CUtensorMap* mA, CUtensorMap* mB,
-                        uint32_t* a_tx) {
+int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& pl, int b_box_rows, CUtensorMap* mA,
+                 CUtensorMap* mB, uint32_t* a_tx) {
   int rc;
   if (o.a_mode == 0) {
     uint64_t dims[2] = {static_cast<uint64_t>(o.ntaps) * o.k_per_tap, static_cast<uint64_t>(o.a_rows)};
@@ -775,18 +685,62 @@ static int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& p
   if (rc) return rc;
   uint64_t bdims[2] = {static_cast<uint64_t>(o.ntaps) * o.k_per_tap, static_cast<uint64_t>(o.b_rows)};
   uint64_t bstr[1] = {static_cast<uint64_t>(o.b_ld) * 2};
-  uint32_t bbox[2] = {kBlockK, static_cast<uint32_t>(pl.block_n)};
+  uint32_t bbox[2] = {kBlockK, static_cast<uint32_t>(b_box_rows)};
   DFU_REQUIRE(o.b_ld >= o.ntaps * o.k_per_tap && o.b_ld % 8 == 0, "gemm: b_ld=%d < ntaps*k_per_tap", o.b_ld);
   return make_tmap_f16(mB, o.b, 2, bdims, bstr, bbox);
 }
 
 static long long g_stats[6] = {0, 0, 0, 0, 0, 0};  // launches, split launches, fused second stages, reduce launches,
-                                                  // last per_sm, last grid
+                                                  // pair-kernel launches, last grid
+
+void fill_group_dev(const DfuGemmOperand& o, GroupDev& G) {
+  G.a_mode = o.a_mode;
+  G.ntaps = o.ntaps;
+  G.nchunks = o.k_per_tap / kBlockK;
+  G.a_plane = o.a_plane;
+  G.b_plane = o.b_plane;
+  G.kb_per_pass = o.ntaps * G.nchunks;
+  G.b_static = o.b_static;
+  for (int t = 0; t < 9; ++t) {
+    G.dn[t] = o.tap_dn[t];
+    G.dy[t] = o.tap_dy[t];
+    G.dx[t] = o.tap_dx[t];
+  }
+}
+
+void fill_epi_params(const DfuGemm* d, EpiParams& e) {
+  e.M = d->m;
+  e.N = d->n;
+  e.epi = d->epi;
+  e.alpha = d->alpha;
+  e.bias = d->bias;
+  e.rowvec = d->rowvec;
+  e.rowvec_ld = d->rowvec_ld;
+  e.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  e.residual = d->residual;
+  e.ldr = d->ldr;
+  e.out_f32 = d->out_f32;
+  e.ldo = d->ldo;
+  e.out_f16 = static_cast<__half*>(d->out_f16);
+  e.ldh = d->ldh;
+  e.out_planes = d->out_planes > 0 ? d->out_planes : 1;
+  e.out_plane_stride = d->out_plane_stride;
+}
 
 static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   Plan pl;
   int rc = plan_gemm(d, &pl);
   if (rc) return rc;
+  if (pl.pair) {
+    DFU_REQUIRE(d->epi >= 0 && d->epi <= 2, "gemm: bad epi");
+    if (d->epi == DFU_EPI_F32) DFU_REQUIRE(d->out_f32 && d->ldo % 4 == 0, "gemm: out_f32/ldo");
+    if (d->epi != DFU_EPI_F32) DFU_REQUIRE(d->out_f16 && d->ldh % 8 == 0, "gemm: out_f16/ldh");
+    if (d->residual) DFU_REQUIRE(d->ldr % 4 == 0, "gemm: ldr");
+    if (d->rowvec) DFU_REQUIRE(d->rows_per_sample > 0 && d->rowvec_ld % 4 == 0, "gemm: rowvec");
+    g_stats[0]++;
+    g_stats[4]++;
+    return run_gemm2(d, pl, stream);
+  }
   if (pl.splits > 1) {
     if (!d->workspace || d->workspace_bytes < pl.ws_bytes) {
       set_error("gemm: split-K needs %zu workspace bytes, got %zu", pl.ws_bytes, d->workspace_bytes);
@@ -803,22 +757,9 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   GemmKernelParams p;
   memset(&p, 0, sizeof(p));
   for (int g = 0; g < d->ngroups; ++g) {
-    rc = encode_group(d, d->g[g], pl, &mA[g], &mB[g], &p.a_tx_bytes[g]);
+    rc = encode_group(d, d->g[g], pl, pl.block_n, &mA[g], &mB[g], &p.a_tx_bytes[g]);
     if (rc) return rc;
-    const DfuGemmOperand& o = d->g[g];
-    GroupDev& G = p.g[g];
-    G.a_mode = o.a_mode;
-    G.ntaps = o.ntaps;
-    G.nchunks = o.k_per_tap / kBlockK;
-    G.a_plane = o.a_plane;
-    G.b_plane = o.b_plane;
-    G.kb_per_pass = o.ntaps * G.nchunks;
-    G.b_static = o.b_static;
-    for (int t = 0; t < 9; ++t) {
-      G.dn[t] = o.tap_dn[t];
-      G.dy[t] = o.tap_dy[t];
-      G.dx[t] = o.tap_dx[t];
-    }
+    fill_group_dev(d->g[g], p.g[g]);
   }
   if (d->ngroups == 1) {
     mA[1] = mA[0];
@@ -847,22 +788,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   p.tmem_cols = cols;
   p.ws = static_cast<float*>(d->workspace);
   EpiParams& e = p.e;
-  e.M = d->m;
-  e.N = d->n;
-  e.epi = d->epi;
-  e.alpha = d->alpha;
-  e.bias = d->bias;
-  e.rowvec = d->rowvec;
-  e.rowvec_ld = d->rowvec_ld;
-  e.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
-  e.residual = d->residual;
-  e.ldr = d->ldr;
-  e.out_f32 = d->out_f32;
-  e.ldo = d->ldo;
-  e.out_f16 = static_cast<__half*>(d->out_f16);
-  e.ldh = d->ldh;
-  e.out_planes = d->out_planes > 0 ? d->out_planes : 1;
-  e.out_plane_stride = d->out_plane_stride;
+  fill_epi_params(d, e);
 
   if (first_use_on_device(ONCE_GEMM_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -916,7 +842,7 @@ int dfu_gemm_plan(const DfuGemm* desc, int32_t* out) {
   int rc = dfu::plan_gemm(desc, &pl);
   if (rc) return rc;
   out[0] = pl.block_n; out[1] = pl.splits; out[2] = pl.stages; out[3] = pl.tiles_m; out[4] = pl.tiles_n;
-  out[5] = pl.total_kb;
+  out[5] = pl.total_kb; out[6] = pl.pair ? 2 : 1; out[7] = 0;
   return DFU_OK;
 }
 size_t dfu_gemm_workspace(const DfuGemm* desc) {

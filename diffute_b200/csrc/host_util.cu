@@ -4,6 +4,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include "kernels.h"
 
 namespace dfu {
@@ -55,6 +59,23 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     set_error("tensor map base %p not 16-byte aligned", base);
     return DFU_ERR_INVALID;
   }
+  // Encoded maps are cached by (base, rank, dims, strides, box): the engine's buffers are static, so after the first
+  // step every launch finds its 128-byte descriptors here instead of calling into the driver 2-4 times.
+  static std::mutex mu;
+  static std::unordered_map<std::string, CUtensorMap> cache;
+  std::string key(reinterpret_cast<const char*>(&base), sizeof(base));
+  key.append(reinterpret_cast<const char*>(&rank), sizeof(rank));
+  key.append(reinterpret_cast<const char*>(gdim), sizeof(cuuint64_t) * rank);
+  key.append(reinterpret_cast<const char*>(gstr), sizeof(cuuint64_t) * (rank - 1));
+  key.append(reinterpret_cast<const char*>(gbox), sizeof(cuuint32_t) * rank);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return DFU_OK;
+    }
+  }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                    gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -64,6 +85,11 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
               (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), gbox[0],
               rank > 1 ? gbox[1] : 0, rank > 2 ? gbox[2] : 0, rank > 3 ? gbox[3] : 0);
     return DFU_ERR_DRIVER;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 16384) cache.clear();  // bounded: shapes / buffers of a long-lived process may change
+    cache.emplace(std::move(key), *out);
   }
   return DFU_OK;
 }

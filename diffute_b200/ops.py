@@ -299,13 +299,14 @@ def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
     L = lib()
     ws = ws or default_workspace()
     d.sync_words = ws.sync.data_ptr()
-    if d.block_n == 0 and d.splits == 0:
+    if d.block_n == 0 and d.splits == 0 and d.kernel == 0:
         key = gemm_key(d)
         if TUNER is not None and key not in TUNE_TABLE:
             TUNE_TABLE[key] = TUNER(d, ws, key)
         t = TUNE_TABLE.get(key)
-        if t is not None:
-            d.block_n, d.splits, d.stages = t
+        if t is not None:  # (block_n, splits, stages[, kernel]); 3-entry rows were tuned for the tile-per-CTA kernel
+            d.block_n, d.splits, d.stages = t[:3]
+            d.kernel = t[3] if len(t) > 3 else 1
     need = L.dfu_gemm_workspace(C.byref(d))
     if need:
         buf = ws.ensure(need)
@@ -317,10 +318,10 @@ def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
 
 
 def gemm_stats():
-    """{launches, split, fused_second_stage, reduce_launches, last_per_sm, last_grid} since process start."""
+    """{launches, split, fused_second_stage, reduce_launches, pair_kernel, last_grid} since process start."""
     out = (C.c_int64 * 6)()
     lib().dfu_gemm_stats(out)
-    return dict(zip(("launches", "split", "fused_second_stage", "reduce_launches", "last_per_sm", "last_grid"), out))
+    return dict(zip(("launches", "split", "fused_second_stage", "reduce_launches", "pair_kernel", "last_grid"), out))
 
 
 def set_epilogue(d: Gemm, *, out_f32=None, out_f16=None, bias=None, rowvec=None, rows_per_sample=0, residual=None,
@@ -346,7 +347,13 @@ def set_epilogue(d: Gemm, *, out_f32=None, out_f16=None, bias=None, rowvec=None,
         d.out_plane_stride = out_f16.stride(0)
 
 
-def linear(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, *, tune: Tuple[int, int, int] = (0, 0, 0),
+def _set_tune(d: Gemm, tune):
+    """tune = (block_n, splits, stages[, kernel]); zeros = let the library / tuning table decide."""
+    d.block_n, d.splits, d.stages = tune[:3]
+    d.kernel = tune[3] if len(tune) > 3 else 0
+
+
+def linear(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, *, tune: Tuple[int, ...] = (0, 0, 0),
            ws: Optional[Workspace] = None, **epi):
     """a16 [planes, M, K] fp16 operand; w16 packed [planes*n, K]; epilogue kwargs as set_epilogue."""
     planes = planes_of(prec)
@@ -355,13 +362,13 @@ def linear(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, *, tune: Tup
     d.ngroups, d.npass = 1, npass_of(prec)
     matrix_operand(d.g[0], a16, w16, a16.shape[2], planes)
     set_epilogue(d, **epi)
-    d.block_n, d.splits, d.stages = tune
+    _set_tune(d, tune)
     launch_gemm(d, ws)
 
 
 def conv(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, out_grid: Tuple[int, int, int], taps, *,
          imgs_per_plane: Optional[int] = None, shortcut: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-         tune: Tuple[int, int, int] = (0, 0, 0), ws: Optional[Workspace] = None, **epi):
+         tune: Tuple[int, ...] = (0, 0, 0), ws: Optional[Workspace] = None, **epi):
     """Implicit-GEMM conv.  a16 [imgs_total, h, w, c] fp16 operand (planes stacked on dim 0), out_grid = (B, H, W).
 
     shortcut = (raw16 [imgs_total, H, W, c2], wsc16 [planes*n, c2]) fuses the ResnetBlock2D 1x1 conv_shortcut as a
@@ -378,7 +385,7 @@ def conv(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, out_grid: Tupl
         raw16, wsc16 = shortcut
         image_operand(d.g[1], raw16, wsc16, planes, [(0, 0, 0)], raw16.shape[0] // planes)
     set_epilogue(d, **epi)
-    d.block_n, d.splits, d.stages = tune
+    _set_tune(d, tune)
     launch_gemm(d, ws)
 
 

@@ -98,6 +98,9 @@ typedef struct DfuGemm {
   int32_t block_n;         /* multiple of 16 (32 for GEGLU), <= 256, divides n */
   int32_t splits;          /* split-K factor */
   int32_t stages;
+  int32_t kernel;          /* 0: choose; 1: one 128 x block_n tile per CTA (split-K slices reduce inside a thread-block
+                              cluster); 2: persistent CTA pairs — tcgen05 cta_group::2, 256 x block_n tiles, two TMEM
+                              accumulators so a tile's epilogue overlaps the next tile's main loop (splits must be 1) */
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
   size_t workspace_bytes;
   void* sync_words;        /* reserved (accepted and ignored): backed a grid-barrier second stage that was measured
@@ -105,10 +108,10 @@ typedef struct DfuGemm {
 } DfuGemm;
 
 int dfu_gemm(const DfuGemm* desc, void* stream);
-/* The tiling dfu_gemm would choose: out[6] = {block_n, splits, stages, tiles_m, tiles_n, k_blocks}. No GPU needed. */
+/* The tiling dfu_gemm would choose: out[8] = {block_n, splits, stages, tiles_m, tiles_n, k_blocks, kernel (1|2), 0}. No GPU needed. */
 int dfu_gemm_plan(const DfuGemm* desc, int32_t* out);
 /* Process-wide counters: out[6] = {gemm launches, split-K launches, fused second stages, separate reduce launches,
- * last occupancy per SM, last grid}. */
+ * persistent pair-kernel launches, last grid}. */
 void dfu_gemm_stats(int64_t* out);
 /* Workspace bytes dfu_gemm needs for this descriptor with automatic tiling (0 if none). */
 size_t dfu_gemm_workspace(const DfuGemm* desc);

@@ -22,7 +22,7 @@ class Fake:
         def f(*a):
             if name == "dfu_gemm":
                 d = a[0]._obj
-                out = (C.c_int32 * 6)()
+                out = (C.c_int32 * 8)()
                 real.dfu_gemm_plan(C.byref(d), out)
                 k = sum(d.g[i].ntaps * d.g[i].k_per_tap for i in range(d.ngroups))
                 calls.append(("gemm_tc_kernel", dict(m=d.m, n=d.n, k=k * d.npass, conv=d.conv, epi=d.epi, block_n=out[0],

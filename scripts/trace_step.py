@@ -32,7 +32,7 @@ _lg = ops.launch_gemm
 
 def launch_gemm(d, ws=None):
     _lg(d, ws)
-    plan = (C.c_int32 * 6)()
+    plan = (C.c_int32 * 8)()
     _lib.lib().dfu_gemm_plan(C.byref(d), plan)
     k = sum(d.g[i].ntaps * d.g[i].k_per_tap for i in range(d.ngroups))
     LOG["gemm"].append({"conv": d.conv, "m": d.m, "n": d.n, "k": k, "epi": d.epi, "block_n": plan[0], "splits": plan[1],

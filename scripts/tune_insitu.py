@@ -99,7 +99,14 @@ def candidates(s):
                 out.append((bn, sp, st))
     # prune: drop configurations that leave most of the chip idle unless nothing else exists
     good = [c for c in out if tiles_m(s) * (s["n"] // c[0]) * c[1] >= 48]
-    return good or out
+    good = good or out
+    # persistent CTA-pair kernel (cta_group::2): 256 x bn tiles, no split-K; stages 0 = as deep as shared memory allows
+    for bn in (256, 192, 160, 128, 96, 80, 64):
+        if s["n"] % bn or (s["epi"] == 2 and bn % 32):
+            continue
+        if ((tiles_m(s) + 1) // 2) * (s["n"] // bn) >= 24 and s["kb"] >= 3:
+            good.append((bn, 1, 0, 2))
+    return good
 
 
 def measure(nrep=2):
@@ -144,7 +151,7 @@ def measure(nrep=2):
 for _ in range(2):
     step()
 torch.cuda.synchronize()
-trace.enable(1 << 20 if WHAT == "vae" else 1 << 18)
+trace.enable(1 << 20 if (WHAT == "vae" or B > 1) else 1 << 18)
 base_order, base_costs, base_span = measure()
 print(f"baseline span {base_span:.1f} us, {len(base_order)} gemm launches, {len(SHAPES)} shapes", flush=True)
 base_table = dict(ops.TUNE_TABLE)
@@ -217,9 +224,10 @@ print(f"tuned span {span:.1f} us (baseline {base_span:.1f}); gemm critical-path 
 os.makedirs("gpurun_out", exist_ok=True)
 merged = {k: list(v) for k, v in base_table.items()}
 merged.update(table)
-with open("gpurun_out/tuning_b200.json" if WHAT == "unet" else "gpurun_out/tuning_b200_vae.json", "w") as f:
+OUT = os.environ.get("TUNE_OUT", WHAT)
+with open(f"gpurun_out/tuning_b200_{OUT}.json", "w") as f:
     json.dump({"meta": {"device": torch.cuda.get_device_name(0), "batch": B, "px": px, "method": "in-situ graph replay, in-kernel timestamps (scripts/tune_insitu.py)",
-                        "key": "conv:m:n:k_blocks(64, all passes):epilogue", "value": "[block_n, splits, stages]",
+                        "key": "conv:m:n:k_blocks(64, all passes):epilogue", "value": "[block_n, splits, stages(, kernel: 1 tile-per-CTA, 2 persistent CTA pairs)]",
                         "span_us": span, "baseline_span_us": base_span}, "table": merged}, f, indent=0)
-with open(f"gpurun_out/tune_insitu_log_{WHAT}.json", "w") as f:
+with open(f"gpurun_out/tune_insitu_log_{OUT}.json", "w") as f:
     json.dump({k: {str(cfg): v for cfg, v in RESULT[k].items()} for k in RESULT}, f)

@@ -47,6 +47,14 @@ def _tol(prec, ops):
     (300, 640, 2560, (64, 8, 4)),        # ragged M + cluster reduce
     (256, 1280, 5120, (160, 6, 3)),      # other split counts go through the workspace + reduce kernel
     (128, 32, 64, (32, 1, 2)),           # single k-block
+    # ---- persistent CTA-pair kernel (cta_group::2, two TMEM accumulators): tune[3] = 2 ----
+    (4096, 320, 320, (160, 1, 0, 2)),    # 32 pair tiles
+    (4096, 320, 320, (64, 1, 3, 2)),     # 80 pair tiles on 74 pairs: some pairs run two tiles (accumulator ping-pong)
+    (1100, 640, 1024, (128, 1, 4, 2)),   # ragged M, odd number of 128-row tiles: the last pair's peer tile is empty
+    (128, 32, 64, (32, 1, 2, 2)),        # one tile, one k-block, block_n = 32: half of the epilogue warps own no chunk
+    (20000, 256, 512, (256, 1, 0, 2)),   # 79 tiles of 256 x 256: both accumulators = all 512 TMEM columns
+    (40000, 320, 192, (80, 1, 0, 2)),    # 628 tiles: ~8.5 tiles per pair, 3 k-blocks each (ring wraps across tiles)
+    (70000, 128, 128, (0, 0, 0)),        # automatic choice picks the pair kernel when its tiles alone fill the GPU
 ])
 def test_linear_f32_epilogue(ops, prec, M, N, K, tune):
     planes = ops.planes_of(prec)
@@ -85,6 +93,10 @@ def test_linear_f16_and_geglu_epilogues(ops, prec):
     got = _recombine(out16)
     tol = 1e-3 if prec == 1 else ACC_TOL  # fp16 output rounding
     assert ((got - ref).abs().max() / ref.abs().max()).item() < tol
+    out16.zero_()
+    ops.linear(a16, w16, 3 * C, prec, tune=(192, 1, 0, 2), out_f16=out16, alpha=0.125)   # pair kernel, f16 planes out
+    torch.cuda.synchronize()
+    assert ((_recombine(out16) - ref).abs().max() / ref.abs().max()).item() < tol
     # GEGLU
     wg = _rand((8 * C, C), 7, C ** -0.5)
     bg = _rand((8 * C,), 8, 0.1)
@@ -94,7 +106,9 @@ def test_linear_f16_and_geglu_epilogues(ops, prec):
     p = _recombine(a16) @ wr.T + bg.double()
     refg = p[:, :4 * C] * F.gelu(p[:, 4 * C:])
     tol = 1.5e-3 if prec == 1 else ACC_TOL
-    for tune in ((0, 0, 0), (160, 2, 3), (128, 3, 3)):   # single pass, cluster split-K, workspace split-K
+    # single pass, cluster split-K, workspace split-K, persistent CTA pairs (block_n 160: the pair splits the weight
+    # tile at 80 rows, inside a 16/16 value/gate block; 256: full TMEM)
+    for tune in ((0, 0, 0), (160, 2, 3), (128, 3, 3), (160, 1, 0, 2), (256, 1, 0, 2)):
         outg = torch.zeros((planes, M, 4 * C), dtype=torch.float16, device="cuda")
         ops.linear(a16, wg16, 8 * C, prec, tune=tune, out_f16=outg, bias=bgi, geglu=True)
         torch.cuda.synchronize()
@@ -136,7 +150,8 @@ def test_conv3x3_stride1(ops, prec, B, H, W, Cin, Cout):
     wr = ops.split_f16(w, planes).double().sum(0)
     ref = _conv_ref(xr, wr, 1, 1) + bias.double() + temb.double()[:, None, None, :]
     bn = 160 if Cout % 160 == 0 else (128 if Cout % 128 == 0 else 64)
-    for tune in ((0, 0, 0), (bn, 4, 3)):   # automatic tiling, then a forced 4-way cluster split-K
+    # automatic tiling, a forced 4-way cluster split-K, the persistent CTA-pair kernel
+    for tune in ((0, 0, 0), (bn, 4, 3), (bn, 1, 0, 2), (64, 1, 0, 2)):
         out.fill_(float("nan"))
         ops.conv(x16, w16, Cout, prec, (B, H, W), ops.taps_3x3_s1(), tune=tune, out_f32=out.view(B * H * W, Cout),
                  bias=bias, rowvec=temb, rows_per_sample=H * W)
@@ -159,12 +174,14 @@ def test_conv3x3_stride2_parity_planes(ops, prec, mode):
     w16 = ops.pack_conv_weight(w, planes)
     out = torch.full((B, H // 2, W // 2, C), float("nan"), device="cuda")
     pad_lo = 1 if mode == "unet" else 0
-    ops.conv(a16, w16, C, prec, (B, H // 2, W // 2), ops.taps_3x3_s2(B, pad_lo), imgs_per_plane=4 * B,
-             out_f32=out.view(-1, C))
-    torch.cuda.synchronize()
     ref = _conv_ref(xs.double().sum(0), ops.split_f16(w, planes).double().sum(0), 2, 1 if mode == "unet" else "asym")
-    err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
-    assert err < ACC_TOL, err
+    for tune in ((0, 0, 0), (128, 1, 0, 2)):
+        out.fill_(float("nan"))
+        ops.conv(a16, w16, C, prec, (B, H // 2, W // 2), ops.taps_3x3_s2(B, pad_lo), imgs_per_plane=4 * B, tune=tune,
+                 out_f32=out.view(-1, C))
+        torch.cuda.synchronize()
+        err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < ACC_TOL, (tune, err)
 
 
 @pytest.mark.parametrize("prec", [1, 2])
@@ -179,10 +196,12 @@ def test_conv_with_fused_shortcut_and_residual(ops, prec):
     h16 = ops.split_f16(h, planes).reshape(planes * B, H, W, Cout)
     x16 = ops.split_f16(xraw, planes).reshape(planes * B, H, W, Cin)
     out = torch.full((B * H * W, Cout), float("nan"), device="cuda")
-    ops.conv(h16, ops.pack_conv_weight(w2, planes), Cout, prec, (B, H, W), ops.taps_3x3_s1(),
-             shortcut=(x16, ops.pack_conv_weight(wsc, planes)), out_f32=out, bias=bias)
-    torch.cuda.synchronize()
     rs = lambda t: ops.split_f16(t, planes).double().sum(0)
     ref = _conv_ref(rs(h), rs(w2), 1, 1) + _conv_ref(rs(xraw), rs(wsc), 1, 0) + bias.double()
-    err = ((out.view(B, H, W, Cout).double() - ref).abs().max() / ref.abs().max()).item()
-    assert err < ACC_TOL, err
+    for tune in ((0, 0, 0), (160, 1, 0, 2)):   # second operand group through both kernels
+        out.fill_(float("nan"))
+        ops.conv(h16, ops.pack_conv_weight(w2, planes), Cout, prec, (B, H, W), ops.taps_3x3_s1(), tune=tune,
+                 shortcut=(x16, ops.pack_conv_weight(wsc, planes)), out_f32=out, bias=bias)
+        torch.cuda.synchronize()
+        err = ((out.view(B, H, W, Cout).double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < ACC_TOL, (tune, err)

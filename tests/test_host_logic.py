@@ -238,16 +238,16 @@ def test_gemm_plan_tilings_without_gpu():
     import ctypes as C
     from diffute_b200 import _lib
     L = _lib.lib()
-    out = (C.c_int32 * 6)()
+    out = (C.c_int32 * 8)()
 
-    def plan(m, n, k, npass=1, conv=0, hw=None, epi=0, tune=(0, 0, 0), taps=1):
+    def plan(m, n, k, npass=1, conv=0, hw=None, epi=0, tune=(0, 0, 0), taps=1, kernel=0):
         d = _lib.Gemm()
         d.m, d.n, d.ngroups, d.npass, d.epi = m, n, 1, npass, epi
         d.g[0].ntaps, d.g[0].k_per_tap = taps, k
         if conv:
             d.conv, d.B, d.H, d.W = 1, 1, hw, hw
             d.g[0].a_mode, d.g[0].a_c = 1, k
-        d.block_n, d.splits, d.stages = tune
+        d.block_n, d.splits, d.stages, d.kernel = (*tune, kernel)
         rc = L.dfu_gemm_plan(C.byref(d), out)
         return rc, list(out)
 
@@ -255,7 +255,7 @@ def test_gemm_plan_tilings_without_gpu():
                                     (256, 1280, 1280, 9, 1, 16), (64, 1280, 1280, 9, 1, 8), (4096, 2560, 320, 1, 0, None),
                                     (262144, 128, 128, 9, 1, 512)]:
         for npass in (1, 3):
-            rc, (bn, sp, st, tm, tn, kb) = plan(m, n, k, npass, conv, hw, taps=taps)
+            rc, (bn, sp, st, tm, tn, kb, kern, _) = plan(m, n, k, npass, conv, hw, taps=taps, kernel=1)
             assert rc == 0, L.dfu_last_error()
             assert kb == taps * k // 64                      # k-blocks counted once, also for the 3-pass mode
             assert bn % 16 == 0 and n % bn == 0 and tn == n // bn and tm == -(-m // 128)
