@@ -115,6 +115,7 @@ SIGNATURES = {
     "dfu_transpose_f16": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _i64, _vp]),
     "dfu_pack_weights": (_i, [_vp, _vp, _i, _i64, _vp]),
     "dfu_trace_set_gemm": (_i, [_vp]),
+    "dfu_trace_set_gemm2": (_i, [_vp]),
     "dfu_trace_set_attn": (_i, [_vp]),
     "dfu_trace_set_norm": (_i, [_vp]),
     "dfu_trace_set_misc": (_i, [_vp]),

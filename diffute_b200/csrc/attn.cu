@@ -97,7 +97,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t& o_free = bars[26];   // 256 arrivals: both accumulators of a finished segment have been read
   uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 27);
 
-  const int warp = threadIdx.x >> 5;
+  // (through a shuffle: provably warp-uniform — the producer / issuer loops are then uniform control flow and ptxas keeps
+  // TMA / MMA operands in uniform registers instead of an ELECT + R2UR.BROADCAST waterfall per instruction)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const long long u_begin = attn_range_begin(p, blockIdx.x);
   const long long u_end = attn_range_begin(p, blockIdx.x + 1);
@@ -156,35 +158,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   if (warp == 8) {
-    // ===== TMA producer ======================================================================
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp walks the schedule, one elected lane issues =============
+    {
       int g = 0, seg = 0;
       for (long long u = u_begin; u < u_end; ++seg) {
         int item, jb0, n, b, head, q0;
         seg_of(u, item, jb0, n);
         coords(item, b, head, q0);
         if (seg > 0) mbar_wait_ns(&q_free, (seg - 1) & 1, 64, 512);  // previous segment's Q K^T MMAs have all read Q
-        mbar_arrive_expect_tx(&q_full, planes * kTile);
-        for (int pl = 0; pl < planes; ++pl)
-          tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full, planes * kTile);
+          for (int pl = 0; pl < planes; ++pl)
+            tma_load_4d(sQ + pl * kTile, &tmQ, &q_full, p.q_col0 + head * kD, q0, b, pl);
+        }
+        __syncwarp();
         for (int j = 0; j < n; ++j, ++g) {
           const int slot = g % kRing;
           const uint32_t par = ((g / kRing) & 1) ^ 1u;
           mbar_wait_ns(&k_empty[slot], par, 64, 512);  // (a polling warp takes issue slots from the softmax warps)
-          mbar_arrive_expect_tx(&k_full[slot], planes * kKvTile);
-          for (int pl = 0; pl < planes; ++pl)
-            tma_load_4d(sK + (slot * planes + pl) * kKvTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&k_full[slot], planes * kKvTile);
+            for (int pl = 0; pl < planes; ++pl)
+              tma_load_4d(sK + (slot * planes + pl) * kKvTile, &tmK, &k_full[slot], p.k_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+          }
+          __syncwarp();
           mbar_wait_ns(&v_empty[slot], par, 64, 512);
-          mbar_arrive_expect_tx(&v_full[slot], planes * kKvTile);
-          for (int pl = 0; pl < planes; ++pl)
-            tma_load_4d(sV + (slot * planes + pl) * kKvTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&v_full[slot], planes * kKvTile);
+            for (int pl = 0; pl < planes; ++pl)
+              tma_load_4d(sV + (slot * planes + pl) * kKvTile, &tmV, &v_full[slot], p.v_col0 + head * kD, (jb0 + j) * kBKV, b, pl);
+          }
+          __syncwarp();
         }
         u += n;
       }
     }
   } else if (warp == 9) {
-    // ===== MMA issuer ========================================================================
-    if (lane == 0) {
+    // ===== MMA issuer: whole warp in uniform control flow, one elected lane issues ==============
+    {
       const uint32_t idesc_qk = umma_idesc_f16(128, kBKV, 0);
       const uint32_t idesc_pv = umma_idesc_f16(128, kD, 1);  // B (= V) is MN-major
       const int npass = planes == 2 ? 3 : 1;
@@ -194,20 +205,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&k_full[slot], (gg / kRing) & 1);
         if (c > 0) mbar_wait(&s_free[h], (c - 1) & 1);  // the warpgroup has read its previous block out of S_h
         tc_fence_after();
-        uint32_t acc = 0;
-        for (int ps = 0; ps < npass; ++ps) {
-          const int qa = (ps == 1) ? 1 : 0, kb = (ps == 2) ? 1 : 0;
-          const uint64_t ad = umma_desc_sw128(smem_u32(sQ + qa * kTile));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sK + (slot * planes + kb) * kKvTile));
+        if (elect_one()) {
+          uint32_t acc = 0;
+          for (int ps = 0; ps < npass; ++ps) {
+            const int qa = (ps == 1) ? 1 : 0, kb = (ps == 2) ? 1 : 0;
+            const uint64_t ad = umma_desc_sw128(smem_u32(sQ + qa * kTile));
+            const uint64_t bd = umma_desc_sw128(smem_u32(sK + (slot * planes + kb) * kKvTile));
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k) {
-            umma_f16_ss(tmem_S + 64 * h, ad + 2 * k, bd + 2 * k, idesc_qk, acc);
-            acc = 1;
+            for (int k = 0; k < kD / 16; ++k) {
+              umma_f16_ss(tmem_S + 64 * h, ad + 2 * k, bd + 2 * k, idesc_qk, acc);
+              acc = 1;
+            }
           }
+          umma_commit(&s_full[h]);
+          umma_commit(&k_empty[slot]);
+          if (last_of_segment) umma_commit(&q_free);
         }
-        umma_commit(&s_full[h]);
-        umma_commit(&k_empty[slot]);
-        if (last_of_segment) umma_commit(&q_free);
+        __syncwarp();
       };
       int g = 0, seg = 0;
       for (long long u = u_begin; u < u_end; ++seg) {
@@ -225,21 +239,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(&v_full[slot], (gg / kRing) & 1);
           if (j == 0 && seg > 0) mbar_wait(&o_free, (seg - 1) & 1);  // the previous item's accumulators were read
           tc_fence_after();
-          uint32_t acc = j >= 2 ? 1u : 0u;  // O_h accumulates in TMEM over the warpgroup's blocks of a segment
-          for (int ps = 0; ps < npass; ++ps) {
-            const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
-            const uint32_t pbase = smem_u32(sP + (pa * 2 + h) * kTile);
-            const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kKvTile);
+          if (elect_one()) {
+            uint32_t acc = j >= 2 ? 1u : 0u;  // O_h accumulates in TMEM over the warpgroup's blocks of a segment
+            for (int ps = 0; ps < npass; ++ps) {
+              const int pa = (ps == 1) ? 1 : 0, vb = (ps == 2) ? 1 : 0;
+              const uint32_t pbase = smem_u32(sP + (pa * 2 + h) * kTile);
+              const uint32_t vbase = smem_u32(sV + (slot * planes + vb) * kKvTile);
 #pragma unroll
-            for (int k = 0; k < kBKV / 16; ++k) {
-              const uint64_t ad = umma_desc_sw128(pbase) + 2 * k;
-              const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
-              umma_f16_ss(tmem_O + 64 * h, ad, bd, idesc_pv, acc);
-              acc = 1;
+              for (int k = 0; k < kBKV / 16; ++k) {
+                const uint64_t ad = umma_desc_sw128(pbase) + 2 * k;
+                const uint64_t bd = umma_desc_sw128(vbase + k * 2048);
+                umma_f16_ss(tmem_O + 64 * h, ad, bd, idesc_pv, acc);
+                acc = 1;
+              }
             }
+            umma_commit(&o_full[h]);
+            umma_commit(&v_empty[slot]);
           }
-          umma_commit(&o_full[h]);
-          umma_commit(&v_empty[slot]);
+          __syncwarp();
         }
         g += n;
         u += n;

@@ -121,9 +121,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // ----------------------------------------------------------------------------------------------
 // In-kernel timeline tracing (only in the -DDFU_TRACE build, libdiffute_b200_trace.so; the product library compiles
-// these macros to nothing).  One 12 x u64 record per CTA: [0] %gridid, [1] tag | bid << 32, [2] smid | nctas << 32,
+// these macros to nothing).  One 16 x u64 record per CTA: [0] %gridid, [1] tag | bid << 32, [2] smid | nctas << 32,
 // [3] globaltimer at entry, [4] clock64 at entry, [5..9] clock64 phase marks, [10] clock64 at exit, [11] globaltimer
-// at exit.  g_tr[0] = next record index (atomic), g_tr[1] = capacity, records start at g_tr + 8.
+// at exit, [12..15] extra clock64 marks.  g_tr[0] = next record index (atomic), g_tr[1] = capacity, records start at g_tr + 8.
 // ----------------------------------------------------------------------------------------------
 #ifdef DFU_TRACE
 static __device__ unsigned long long* g_tr = nullptr;
@@ -137,7 +137,7 @@ __device__ __forceinline__ unsigned long long* trace_begin(unsigned int tag) {
   if (!base) return nullptr;
   const unsigned long long idx = atomicAdd(base, 1ull);
   if (idx >= base[1]) return nullptr;
-  unsigned long long* r = base + 8 + idx * 12;
+  unsigned long long* r = base + 8 + idx * 16;
   unsigned long long gid;
   unsigned int smid;
   asm volatile("mov.u64 %0, %%gridid;" : "=l"(gid));
@@ -149,7 +149,7 @@ __device__ __forceinline__ unsigned long long* trace_begin(unsigned int tag) {
   r[3] = trace_gtime();
   r[4] = clock64();
 #pragma unroll
-  for (int i = 5; i < 12; ++i) r[i] = 0;
+  for (int i = 5; i < 16; ++i) r[i] = 0;
   return r;
 }
 __device__ __forceinline__ void trace_mark(unsigned long long* r, int slot) {

@@ -70,7 +70,11 @@ __device__ __forceinline__ void reduce_quad(const float* __restrict__ ws, int sp
 template <int S>
 __device__ __forceinline__ void cluster_reduce(const GemmKernelParams& p, const uint8_t* smem, int split, int n_tile0,
                                                int m0, int x0, int y0, int img0) {
-  constexpr int rows_per = kBlockM / S;
+  // Only the rows the tile really has are reduced, split evenly over the S CTAs (a 64-pixel map fills half a tile: with
+  // a fixed 128 / S rows per CTA half of the cluster would idle through the reduction).
+  const int tile_rows = p.conv ? p.bw * p.bh * p.bn : min(kBlockM, p.e.M - m0);
+  const int rows_per = (tile_rows + S - 1) / S;
+  constexpr int CH = S < 8 ? S : 8;  // remote loads in flight per thread (registers: 16 in flight would spill)
   const bool geglu = p.e.epi == DFU_EPI_GEGLU;
   const int qpr = geglu ? p.block_n / 8 : p.block_n / 4;
   const int ldp = p.block_n + 4;
@@ -81,6 +85,7 @@ __device__ __forceinline__ void cluster_reduce(const GemmKernelParams& p, const 
   const int te = threadIdx.x - 64;
   for (int idx = te; idx < rows_per * qpr; idx += kEpiThreads) {
     const int rr = split * rows_per + idx / qpr;
+    if (rr >= tile_rows) break;
     const int qi = idx % qpr;
     const int col = geglu ? (qi >> 2) * 32 + (qi & 3) * 4 : qi * 4;
     int m;
@@ -102,22 +107,27 @@ __device__ __forceinline__ void cluster_reduce(const GemmKernelParams& p, const 
     if (!geglu && p.e.residual)
       rs = *reinterpret_cast<const float4*>(p.e.residual + static_cast<size_t>(m) * p.e.ldr + n_tile0 + col);
     const uint32_t off = static_cast<uint32_t>(rr * ldp + col) * 4u;
-    float4 t[S], u[S];
-#pragma unroll
-    for (int q = 0; q < S; ++q) t[q] = ld_dsmem_f4(peer[q] + off);
-    if (geglu) {
-#pragma unroll
-      for (int q = 0; q < S; ++q) u[q] = ld_dsmem_f4(peer[q] + off + 64);
-    }
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
 #pragma unroll
-    for (int q = 0; q < S; ++q) {
-      a.x += t[q].x; a.y += t[q].y; a.z += t[q].z; a.w += t[q].w;
+    for (int q0 = 0; q0 < S; q0 += CH) {  // slice order => deterministic
+      float4 t[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) t[q] = ld_dsmem_f4(peer[q0 + q] + off);
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        a.x += t[q].x; a.y += t[q].y; a.z += t[q].z; a.w += t[q].w;
+      }
     }
     if (geglu) {
 #pragma unroll
-      for (int q = 0; q < S; ++q) {
-        g.x += u[q].x; g.y += u[q].y; g.z += u[q].z; g.w += u[q].w;
+      for (int q0 = 0; q0 < S; q0 += CH) {
+        float4 u[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) u[q] = ld_dsmem_f4(peer[q0 + q] + off + 64);
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          g.x += u[q].x; g.y += u[q].y; g.z += u[q].z; g.w += u[q].w;
+        }
       }
       epi_geglu_quad(p.e, m, n_tile0 + col, a, g);
     } else {
@@ -151,7 +161,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t nplane = p.npass == 3 ? 2u : 1u;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   const uint32_t stage_bytes = nplane * (kABytes + b_bytes);
-  const int warp = threadIdx.x >> 5;
+  // (through a shuffle: provably warp-uniform, so the producer / issuer loops below are uniform control flow and ptxas
+  // keeps TMA / MMA operands in uniform registers instead of an ELECT + R2UR.BROADCAST waterfall per instruction)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   // ---- tile coordinates -------------------------------------------------------------------
@@ -208,8 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // first access to data that kernel produced — the TMA producer only after it has requested the weight tiles
 
   if (warp == 0) {
-    // ===== TMA producer =====================================================================
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp walks the k-blocks, one elected lane issues =============
+    {
       const int kbg0 = p.g[0].kb_per_pass;
       // k-block -> (group, tap, channel chunk) and the loads of that k-block (hi [+ lo] tile of each operand)
       auto issue = [&](int kb, int stage, bool load_a, bool load_b) {
@@ -248,18 +260,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // the streaming itself) overlaps the producer kernel's tail.
       const bool pre = p.g[0].b_static && (p.ngroups == 1 || p.g[1].b_static);
       const int npre = pre ? min(p.stages, kb1 - kb0) : 0;
-      for (int i = 0; i < npre; ++i) issue(kb0 + i, i, false, true);
+      if (elect_one())
+        for (int i = 0; i < npre; ++i) issue(kb0 + i, i, false, true);
+      __syncwarp();
       pdl_wait();  // activations (A) are valid from here on
-      DFU_TR_SHARED_MARK(6);
+      if (lane == 0) DFU_TR_SHARED_MARK(6);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (kb - kb0 < npre) {
-          issue(kb, stage, true, false);
+          if (elect_one()) issue(kb, stage, true, false);
         } else {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          issue(kb, stage, true, true);
+          if (elect_one()) issue(kb, stage, true, true);
         }
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -267,35 +282,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =======================================================================
-    if (lane == 0) {
+    // ===== MMA issuer: whole warp in uniform control flow, one elected lane issues ============
+    {
       const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (kb == kb0) DFU_TR_SHARED_MARK(7);
+        if (lane == 0 && kb == kb0) DFU_TR_SHARED_MARK(7);
         const uint32_t sA = smem_u32(smem + stage * stage_bytes);
         const uint32_t sB = sA + nplane * kABytes;
         const int nprod = p.npass == 3 ? 3 : 1;
-        for (int ps = 0; ps < nprod; ++ps) {  // hi*hi [, lo*hi, hi*lo] from the same stage
-          const uint64_t adesc = umma_desc_sw128(sA + (ps == 1 ? kABytes : 0u));
-          const uint64_t bdesc = umma_desc_sw128(sB + (ps == 2 ? b_bytes : 0u));
+        if (elect_one()) {
+          for (int ps = 0; ps < nprod; ++ps) {  // hi*hi [, lo*hi, hi*lo] from the same stage
+            const uint64_t adesc = umma_desc_sw128(sA + (ps == 1 ? kABytes : 0u));
+            const uint64_t bdesc = umma_desc_sw128(sB + (ps == 2 ? b_bytes : 0u));
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-            umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                        (kb > kb0 || ps > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+              umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > kb0 || ps > 0 || k > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);  // frees this smem slot when the MMAs above have read it
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem slot when the MMAs above have read it
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&tmem_full_bar);  // accumulator complete
+      if (elect_one()) umma_commit(&tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue warps (2..9) =============================================================
@@ -374,6 +393,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t raw[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
       tmem_ld_wait();
+      if (threadIdx.x == 64 && c == 0) DFU_TR_SHARED_MARK(12);
       const int ncol = p.block_n - c;  // columns of this chunk inside the tile (block_n may end mid-chunk)
       if (p.cluster > 1) {
         // cluster split-K: park this slice's fp32 partial tile in OWN shared memory (row r at r * (block_n + 4))
@@ -471,6 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (c + 64 < p.block_n) res[it] = fetch_res1(c + 64, it);
         }
       }
+      if (threadIdx.x == 64 && c == 0) DFU_TR_SHARED_MARK(13);
     }
     if (threadIdx.x == 64) DFU_TR_SHARED_MARK(9);
   }
@@ -483,7 +504,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       switch (p.cluster) {
         case 2: cluster_reduce<2>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
         case 4: cluster_reduce<4>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
-        default: cluster_reduce<8>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
+        case 8: cluster_reduce<8>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
+        default: cluster_reduce<16>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
       }
     }
     cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
@@ -792,11 +814,13 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
 
   if (first_use_on_device(ONCE_GEMM_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   const int grid = pl.tiles_m * pl.tiles_n * pl.splits;
   static const bool cluster_ok = !(getenv("DFU_SPLITK_CLUSTER") && getenv("DFU_SPLITK_CLUSTER")[0] == '0');
   p.cluster = 0;
-  if (cluster_ok && (pl.splits == 2 || pl.splits == 4 || pl.splits == 8)) {
+  // (16 CTAs per cluster is above the portable limit of 8: the kernel opts in once per device, below)
+  if (cluster_ok && (pl.splits == 2 || pl.splits == 4 || pl.splits == 8 || pl.splits == 16)) {
     // the partial tile (128 x (block_n + 4) fp32) must fit in the idle operand ring
     const size_t part = static_cast<size_t>(kBlockM) * (pl.block_n + 4) * 4;
     if (part <= pl.smem_bytes - 1024) p.cluster = pl.splits;

@@ -13,6 +13,7 @@
 // Same operand model as gemm.cu (matrix or NHWC-image A walked by taps with TMA out-of-bounds zero fill, two operand
 // groups, 1 or 3 passes over hi/lo planes) and the same fused epilogues; no split-K (the tile count is the parallelism).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gemm_shared.cuh"
@@ -27,11 +28,14 @@ struct Gemm2Params {
   int tiles_n;
   int num_tiles;     // ceil(tiles_m / 2) * tiles_n
   int stages, total_kb, ngroups, npass;
+  int kbs;           // k-blocks (K = 64) per pipeline stage: one full-barrier wait and ONE multicast commit per stage
   GroupDev g[2];
   int conv, B, H, W, bw, bh, bn, tiles_x, tiles_y;
   uint32_t a_tx_bytes[2];
   uint32_t b_tx_bytes;  // per CTA
   uint32_t tmem_cols;   // allocated columns (power of two >= 2 * block_n); accumulator s starts at s * tmem_cols / 2
+  int debug;            // experiments only (DFU_G2_DEBUG): bit 0 = every CTA signals its OWN full barrier (results of the
+                        // peer half are then unsynchronised: timing only)
   EpiParams e;
 };
 
@@ -53,8 +57,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t nplane = p.npass == 3 ? 2u : 1u;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 64u;  // block_n / 2 rows of 128 bytes
-  const uint32_t stage_bytes = nplane * (kABytes + b_bytes);
-  const int warp = threadIdx.x >> 5;
+  const uint32_t kb_bytes = nplane * (kABytes + b_bytes);            // one k-block: [A planes][B planes]
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.kbs) * kb_bytes;
+  const int nsteps = (p.total_kb + p.kbs - 1) / p.kbs;                // pipeline steps per tile
+  // warp index through a shuffle: provably warp-uniform, so that the role loops below are UNIFORM control flow and
+  // ptxas keeps the TMA / MMA operands (descriptors, coordinates, barrier addresses) in uniform registers.  With the
+  // loops under `if (lane == 0)` every UTCHMMA / UTMALDG was preceded by an ELECT + R2UR.BROADCAST "waterfall"
+  // (~250 cycles per MMA, measured: the pair kernel was bound by its single issuing thread, not by the tensor pipe).
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair_id = blockIdx.x >> 1;
@@ -104,39 +114,50 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   };
 
   if (warp == 0) {
-    // ===== TMA producer (both CTAs) ============================================================
-    if (lane == 0) {
+    // ===== TMA producer (both CTAs): the whole warp walks the schedule, one elected lane issues ==
+    {
       const int kbg0 = p.g[0].kb_per_pass;
       int n_tile0, m0, x0, y0, img0;
-      auto issue = [&](int kb, int stage, bool load_a, bool load_b) {
-        int r = kb, gi = 0;
-        if (r >= kbg0) {
-          r -= kbg0;
-          gi = 1;
-        }
-        const GroupDev& G = p.g[gi];
-        const int tap = r / G.nchunks;
-        const int chunk = r - tap * G.nchunks;
-        const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
-        const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
-        uint8_t* sA = smem + stage * stage_bytes;
-        uint8_t* sB = sA + nplane * kABytes;
-        const uint32_t bar = dsmem_addr(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+      // loads of pipeline step `st` of the current tile (k-blocks st*kbs ...) into ring slot `stage`
+      auto issue = [&](int st, int stage, bool load_a, bool load_b) {
+        const int kb0 = st * p.kbs;
+        const int cnt = min(p.kbs, p.total_kb - kb0);
+        const bool localbar = (p.debug & 1) != 0;
+        const uint32_t bar = dsmem_addr(smem_u32(&full_bar[stage]), localbar ? rank : 0);  // the leader's barrier
         if (load_b) {
-          // the leader arms its barrier with the bytes of ALL tiles of the k-block, its own and the peer's
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * nplane * (p.a_tx_bytes[gi] + p.b_tx_bytes));
-          for (uint32_t pl = 0; pl < nplane; ++pl)
-            tma_load_2d_cg2(sB + pl * b_bytes, mB, bar, (tap * G.nchunks + chunk) * kBlockK,
-                            n_tile0 + static_cast<int>(rank) * (p.block_n >> 1) + static_cast<int>(pl) * G.b_plane);
+          // the leader arms its barrier with the bytes of ALL tiles of the step, its own and the peer's
+          uint32_t bytes = 0;
+          for (int j = 0; j < cnt; ++j) bytes += nplane * (p.a_tx_bytes[(kb0 + j) >= kbg0 ? 1 : 0] + p.b_tx_bytes);
+          if (localbar) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          else if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes);
         }
-        if (load_a) {
-          for (uint32_t pl = 0; pl < nplane; ++pl) {
-            const int a_sel = static_cast<int>(pl) * G.a_plane;
-            if (G.a_mode == 0) {
-              tma_load_2d_cg2(sA + pl * kABytes, mA, bar, (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
-            } else {
-              tma_load_4d_cg2(sA + pl * kABytes, mA, bar, chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
-                              img0 + G.dn[tap] + a_sel);
+        for (int j = 0; j < cnt; ++j) {
+          int r = kb0 + j, gi = 0;
+          if (r >= kbg0) {
+            r -= kbg0;
+            gi = 1;
+          }
+          const GroupDev& G = p.g[gi];
+          const int tap = r / G.nchunks;
+          const int chunk = r - tap * G.nchunks;
+          const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
+          const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
+          uint8_t* sA = smem + stage * stage_bytes + j * kb_bytes;
+          uint8_t* sB = sA + nplane * kABytes;
+          if (load_b) {
+            for (uint32_t pl = 0; pl < nplane; ++pl)
+              tma_load_2d_cg2(sB + pl * b_bytes, mB, bar, (tap * G.nchunks + chunk) * kBlockK,
+                              n_tile0 + static_cast<int>(rank) * (p.block_n >> 1) + static_cast<int>(pl) * G.b_plane);
+          }
+          if (load_a) {
+            for (uint32_t pl = 0; pl < nplane; ++pl) {
+              const int a_sel = static_cast<int>(pl) * G.a_plane;
+              if (G.a_mode == 0) {
+                tma_load_2d_cg2(sA + pl * kABytes, mA, bar, (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
+              } else {
+                tma_load_4d_cg2(sA + pl * kABytes, mA, bar, chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
+                                img0 + G.dn[tap] + a_sel);
+              }
             }
           }
         }
@@ -148,20 +169,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       if (pair_id < p.num_tiles) {
         tile_coords(pair_id, n_tile0, m0, x0, y0, img0);
         // weights do not depend on the previous kernel: request the first ring-full of weight tiles before waiting
-        npre = pre ? min(p.stages, p.total_kb) : 0;
-        for (int i = 0; i < npre; ++i) issue(i, i, false, true);
+        npre = pre ? min(p.stages, nsteps) : 0;
+        if (elect_one())
+          for (int i = 0; i < npre; ++i) issue(i, i, false, true);
+        __syncwarp();
       }
       pdl_wait();
-      DFU_TR_SHARED_MARK(6);
+      if (lane == 0) DFU_TR_SHARED_MARK(6);
       for (int tile = pair_id; tile < p.num_tiles; tile += npairs) {
         tile_coords(tile, n_tile0, m0, x0, y0, img0);
-        for (int kb = 0; kb < p.total_kb; ++kb) {
-          if (tile == pair_id && kb < npre) {
-            issue(kb, stage, true, false);
+        for (int st = 0; st < nsteps; ++st) {
+          if (tile == pair_id && st < npre) {
+            if (elect_one()) issue(st, stage, true, false);
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            issue(kb, stage, true, true);
+            if (elect_one()) issue(st, stage, true, true);
           }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -170,8 +194,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA only) =========================================================
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer (leader CTA only): whole warp in uniform control flow, one elected lane issues =
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_f16(2 * kBlockM, p.block_n);
       const int nprod = p.npass == 3 ? 3 : 1;
       int stage = 0;
@@ -182,27 +206,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);  // the pair's epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (p.tmem_cols >> 1);
-        for (int kb = 0; kb < p.total_kb; ++kb) {
+        for (int st = 0; st < nsteps; ++st) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (it == 0 && kb == 0) DFU_TR_SHARED_MARK(7);
-          const uint32_t sA = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sB = sA + nplane * kABytes;
-          for (int ps = 0; ps < nprod; ++ps) {  // hi*hi [, lo*hi, hi*lo] from the same stage
-            const uint64_t adesc = umma_desc_sw128(sA + (ps == 1 ? kABytes : 0u));
-            const uint64_t bdesc = umma_desc_sw128(sB + (ps == 2 ? b_bytes : 0u));
+          if (lane == 0 && it == 0 && st == 0) DFU_TR_SHARED_MARK(7);
+          const int cnt = min(p.kbs, p.total_kb - st * p.kbs);
+          if (elect_one()) {
+            for (int j = 0; j < cnt; ++j) {
+              const uint32_t sA = smem_u32(smem + stage * stage_bytes + j * kb_bytes);
+              const uint32_t sB = sA + nplane * kABytes;
+              for (int ps = 0; ps < nprod; ++ps) {  // hi*hi [, lo*hi, hi*lo] from the same k-block
+                const uint64_t adesc = umma_desc_sw128(sA + (ps == 1 ? kABytes : 0u));
+                const uint64_t bdesc = umma_desc_sw128(sB + (ps == 2 ? b_bytes : 0u));
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16_ss2(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                           (kb > 0 || ps > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16_ss2(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                               (st > 0 || j > 0 || ps > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit2(&empty_bar[stage], 3);  // frees this slot in BOTH CTAs
           }
-          umma_commit2(&empty_bar[stage], 3);  // frees this slot in BOTH CTAs
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit2(&tmem_full_bar[acc], 3);  // accumulator complete, in both CTAs' TMEM
+        if (elect_one()) umma_commit2(&tmem_full_bar[acc], 3);  // accumulator complete, in both CTAs' TMEM
+        __syncwarp();
       }
     }
   } else {
@@ -283,6 +314,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         uint32_t raw[32];
         tmem_ld32(taddr + static_cast<uint32_t>(c), raw);
         tmem_ld_wait();
+        if (threadIdx.x == 64 && it == 0 && c == 0) DFU_TR_SHARED_MARK(12);
         if (c + 64 >= p.block_n) {  // this warp's last read of the accumulator: hand it back to the MMA issuer
           tc_fence_before();
           if (lane == 0) mbar_arrive_cluster(tmem_empty_addr[acc]);
@@ -388,7 +420,13 @@ int run_gemm2(const DfuGemm* d, const Plan& pl, cudaStream_t stream) {
   p.tiles_m = pl.tiles_m;
   p.tiles_n = pl.tiles_n;
   p.num_tiles = ((pl.tiles_m + 1) / 2) * pl.tiles_n;
-  p.stages = pl.stages;
+  // pl.stages counts k-blocks the ring can hold; a pipeline stage groups `kbs` of them
+  static const int kbs_env = getenv("DFU_G2_KBS") ? atoi(getenv("DFU_G2_KBS")) : 0;
+  int kbs = kbs_env > 0 ? kbs_env : 4;  // measured: one full-barrier round trip + multicast commit costs ~0.26 us per stage
+  if (kbs > pl.stages / 2) kbs = pl.stages / 2 > 0 ? pl.stages / 2 : 1;
+  if (kbs > pl.total_kb) kbs = pl.total_kb;
+  p.kbs = kbs;
+  p.stages = pl.stages / kbs;
   p.total_kb = pl.total_kb;
   p.ngroups = d->ngroups;
   p.npass = d->npass;
@@ -406,6 +444,8 @@ int run_gemm2(const DfuGemm* d, const Plan& pl, cudaStream_t stream) {
   while (cols < 2u * static_cast<uint32_t>(pl.block_n)) cols <<= 1;
   p.tmem_cols = cols;
   fill_epi_params(d, p.e);
+  static const int debug = getenv("DFU_G2_DEBUG") ? atoi(getenv("DFU_G2_DEBUG")) : 0;
+  p.debug = debug;
   if (first_use_on_device(ONCE_GEMM2_ATTR))
     DFU_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   const int sms = num_sms() > 0 ? num_sms() : 148;
@@ -417,3 +457,5 @@ int run_gemm2(const DfuGemm* d, const Plan& pl, cudaStream_t stream) {
 }
 
 }  // namespace dfu
+
+DFU_TRACE_SETTER(dfu_trace_set_gemm2)

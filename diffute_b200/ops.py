@@ -418,7 +418,7 @@ def groupnorm(src0: torch.Tensor, gamma, beta, eps: float, silu: bool, prec: int
 def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: torch.Tensor):
     """x [M, C] fp32 -> out16 [planes, M, C]."""
     M, C = x.shape
-    with _Prof('layernorm', 1):
+    with _Prof('layernorm', 1, 0.0, float(M * C) * (4 + 2 * out16.shape[0])):
         check(lib().dfu_layernorm(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
                                   out16.shape[0], out16.stride(0), _stream()), "dfu_layernorm")
 

@@ -17,7 +17,7 @@ from . import _lib
 
 TAGS = {1: "gemm", 2: "splitk_reduce", 3: "attn", 4: "attn_merge", 5: "gn_stats", 6: "gn_finalize", 7: "gn_apply",
         8: "gn_fused", 9: "layernorm", 10: "cast", 11: "temb", 12: "gemv", 13: "conv_in", 14: "conv_out", 15: "misc"}
-REC = 12
+REC = 16
 _buf = None
 
 
@@ -28,7 +28,7 @@ def enable(capacity: int = 1 << 20) -> torch.Tensor:
     _buf = torch.zeros(8 + capacity * REC, dtype=torch.int64, device="cuda")
     _buf[1] = capacity
     torch.cuda.synchronize()
-    for n in ("gemm", "attn", "norm", "misc"):
+    for n in ("gemm", "gemm2", "attn", "norm", "misc"):
         rc = getattr(L, f"dfu_trace_set_{n}")(C.c_void_p(_buf.data_ptr()))
         if rc != 0:
             raise _lib.DfuError("tracing needs the diagnostic library: run with DFU_TRACE=1")
@@ -42,7 +42,7 @@ def reset():
 
 def disable():
     L = _lib.lib()
-    for n in ("gemm", "attn", "norm", "misc"):
+    for n in ("gemm", "gemm2", "attn", "norm", "misc"):
         getattr(L, f"dfu_trace_set_{n}")(None)
 
 
@@ -78,7 +78,8 @@ def collect(sm_mhz: float = 1965.0) -> List[Dict]:
 
         d = {"grid_id": gid, "kernel": TAGS.get(tag, str(tag)), "extra": extra, "ctas": len(idx),
              "nctas": int(rr[0, 2] >> 32), "start_first": float(gt_s.min()), "start_last": float(gt_s.max())}
-        for name, slot in (("setup", 5), ("wait", 6), ("p7", 7), ("p8", 8), ("p9", 9), ("end_clk", 10)):
+        for name, slot in (("setup", 5), ("wait", 6), ("p7", 7), ("p8", 8), ("p9", 9), ("end_clk", 10), ("x12", 12),
+                           ("x13", 13), ("x14", 14), ("x15", 15)):
             v, ok = ph(slot)
             if ok.any():
                 d[name + "_first"] = float(v[ok].min())

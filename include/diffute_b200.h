@@ -233,6 +233,7 @@ int dfu_pack_weights(const DfuPackJob* jobs_dev, const int64_t* prefix_dev, int 
  * in the product library these return -1 and no kernel contains tracing code.  One setter per translation unit.
  */
 int dfu_trace_set_gemm(void* buf);
+int dfu_trace_set_gemm2(void* buf);
 int dfu_trace_set_attn(void* buf);
 int dfu_trace_set_norm(void* buf);
 int dfu_trace_set_misc(void* buf);

@@ -45,6 +45,8 @@ def _tol(prec, ops):
     (256, 1280, 1280, (128, 4, 3)),
     (64, 1280, 5120, (160, 8, 3)),
     (300, 640, 2560, (64, 8, 4)),        # ragged M + cluster reduce
+    (64, 1280, 5120, (128, 16, 3)),      # 16-CTA clusters (non-portable size): half-full tile, 4 rows per CTA
+    (200, 1280, 1280, (64, 16, 2)),      # ragged rows over 16 slices, some slices with a single k-block
     (256, 1280, 5120, (160, 6, 3)),      # other split counts go through the workspace + reduce kernel
     (128, 32, 64, (32, 1, 2)),           # single k-block
     # ---- persistent CTA-pair kernel (cta_group::2, two TMEM accumulators): tune[3] = 2 ----

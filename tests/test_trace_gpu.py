@@ -57,5 +57,5 @@ def test_product_library_has_no_tracing():
         pytest.skip("diagnostic library selected for this process")
     L = _lib.lib()
     buf = torch.zeros(64, dtype=torch.int64, device="cuda")
-    for n in ("gemm", "attn", "norm", "misc"):
+    for n in ("gemm", "gemm2", "attn", "norm", "misc"):
         assert getattr(L, f"dfu_trace_set_{n}")(buf.data_ptr()) == -1
