@@ -413,6 +413,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
                         __uint_as_float(raw[4 * i + 3]));
       __syncwarp();
+      if (threadIdx.x == 64 && c == 0) DFU_TR_SHARED_MARK(14);
       const int n = n_tile0 + c;
       // per-chunk constants of this lane's column quad(s): bias (+ the time-embedding row when the warp's rows belong
       // to one sample) are added with one FFMA per element; nothing per-row is recomputed inside the loops
@@ -488,6 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             else
               store_f16x4(p.e.out_f16 + static_cast<size_t>(mrs[it]) * p.e.ldh + n + cq * 4, o, lo_plane, p.e.out_plane_stride);
           }
+          if (it == 0 && threadIdx.x == 64 && c == 0) DFU_TR_SHARED_MARK(15);
           if (c + 64 < p.block_n) res[it] = fetch_res1(c + 64, it);
         }
       }

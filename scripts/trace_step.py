@@ -107,7 +107,8 @@ for i, d in enumerate(rows):
     if d["kernel"] == "gemm":
         ph = (f"pro {d.get('setup_med', 0) - d['start_first']:5.1f} ff {d.get('p7_med', w0) - w0:5.1f} mma {d.get('p8_med', w0) - w0:5.1f} "
               f"epi {d.get('p9_med', w0) - w0:5.1f} end {d.get('end_clk_med', w0) - w0:5.1f}"
-              f" [ld {d.get('x12_med', w0) - w0:4.1f} c1 {d.get('x13_med', w0) - w0:4.1f}]")
+              f" [ld {d.get('x12_med', w0) - w0:4.1f} stg {d.get('x14_med', w0) - w0:4.1f} st1 {d.get('x15_med', w0) - w0:4.1f}"
+              f" c1 {d.get('x13_med', w0) - w0:4.1f}]")
     elif d["kernel"] == "attn":
         ph = f"pro {d.get('setup_med', 0) - d['start_first']:5.1f} main {d.get('p8_med', w0) - w0:5.1f} end {d.get('end_clk_med', w0) - w0:5.1f}"
     print(f"{i:4d} {d['kernel']:13} {d['nctas']:5d} {d['start_first']:8.1f} {d.get('wait_first', 0):8.1f} {d['gap']:6.1f} {d['body']:7.1f} | {ph} | {d['info']}")
