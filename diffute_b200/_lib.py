@@ -32,7 +32,7 @@ class Gemm(C.Structure):
         ("m", C.c_int32), ("n", C.c_int32), ("ngroups", C.c_int32), ("npass", C.c_int32),
         ("g", GemmOperand * 2),
         ("conv", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-        ("epi", C.c_int32), ("alpha", C.c_float),
+        ("epi", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float),
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int32), ("rows_per_sample", C.c_int32),
         ("residual", C.c_void_p), ("ldr", C.c_int32),
         ("out_f32", C.c_void_p), ("ldo", C.c_int32),
@@ -96,7 +96,8 @@ SIGNATURES = {
     "dfu_groupnorm_workspace": (_sz, [_i, _i, _i, _i]),
     "dfu_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp,
                            _vp]),
-    "dfu_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _i, _i64, _vp]),
+    "dfu_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _i, _i64, _vp, _vp]),
+    "dfu_patchify_f16": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     "dfu_cast_f16": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i64, _vp]),
     "dfu_timestep_embedding": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "dfu_gemv": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),

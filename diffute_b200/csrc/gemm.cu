@@ -469,6 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool per_row_vec = p.e.rowvec != nullptr && !one_sample;
         const bool f32_out = p.e.epi == DFU_EPI_F32;
         const bool lo_plane = p.e.out_planes > 1;
+        const bool act = p.e.act != 0;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
@@ -483,6 +484,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const float4 t = __ldg(reinterpret_cast<const float4*>(
                   p.e.rowvec + static_cast<size_t>(mrs[it] / p.e.rows_per_sample) * p.e.rowvec_ld + n + cq * 4));
               o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            if (act) {
+              o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w);
             }
             if (f32_out)
               *reinterpret_cast<float4*>(p.e.out_f32 + static_cast<size_t>(mrs[it]) * p.e.ldo + n + cq * 4) = o;
@@ -736,6 +740,7 @@ void fill_epi_params(const DfuGemm* d, EpiParams& e) {
   e.M = d->m;
   e.N = d->n;
   e.epi = d->epi;
+  e.act = d->act;
   e.alpha = d->alpha;
   e.bias = d->bias;
   e.rowvec = d->rowvec;
@@ -772,6 +777,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     }
   }
   DFU_REQUIRE(d->epi >= 0 && d->epi <= 2, "gemm: bad epi");
+  DFU_REQUIRE(d->act == 0 || (d->act == 1 && d->epi != DFU_EPI_GEGLU), "gemm: act=%d (GEGLU has its own gate)", d->act);
   if (d->epi == DFU_EPI_F32) DFU_REQUIRE(d->out_f32 && d->ldo % 4 == 0, "gemm: out_f32/ldo");
   if (d->epi != DFU_EPI_F32) DFU_REQUIRE(d->out_f16 && d->ldh % 8 == 0, "gemm: out_f16/ldh");
   if (d->residual) DFU_REQUIRE(d->ldr % 4 == 0, "gemm: ldr");

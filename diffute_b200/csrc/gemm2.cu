@@ -246,6 +246,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const bool has_res = !geglu && e.residual != nullptr;
     const bool f32_out = e.epi == DFU_EPI_F32;
     const bool lo_plane = e.out_planes > 1;
+    const bool act = e.act != 0;
     const float alpha = e.alpha;
     const int cq = lane & 7;
     const int cq4 = lane & 3;
@@ -374,6 +375,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 const float4 t = __ldg(reinterpret_cast<const float4*>(
                     e.rowvec + static_cast<size_t>(mrs[i] / e.rows_per_sample) * e.rowvec_ld + n + cq * 4));
                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+              }
+              if (act) {
+                o.x = gelu_erf_f(o.x); o.y = gelu_erf_f(o.y); o.z = gelu_erf_f(o.z); o.w = gelu_erf_f(o.w);
               }
               if (f32_out)
                 *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(mrs[i]) * e.ldo + n + cq * 4) = o;

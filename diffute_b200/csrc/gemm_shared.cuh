@@ -23,6 +23,7 @@ struct GroupDev {
 struct EpiParams {
   int M, N;
   int epi;
+  int act;  // 1: exact-erf GELU on the finished value
   float alpha;
   const float* bias;
   const float* rowvec;
@@ -97,6 +98,9 @@ __device__ __forceinline__ void epi_quad_res(const EpiParams& e, int m, int n, f
                                              const float* sbias = nullptr, int n_tile0 = 0) {
   v = epi_affine(e, m, n, v, sbias, n_tile0);
   v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  if (e.act) {
+    v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w);
+  }
   if (e.epi == DFU_EPI_F32) {
     *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;
   } else {
@@ -109,6 +113,9 @@ __device__ __forceinline__ void epi_quad(const EpiParams& e, int m, int n, float
   if (e.residual) {
     const float4 t = *reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(m) * e.ldr + n);
     v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  }
+  if (e.act) {
+    v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w);
   }
   if (e.epi == DFU_EPI_F32) {
     *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(m) * e.ldo + n) = v;

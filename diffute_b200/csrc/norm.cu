@@ -402,7 +402,7 @@ constexpr int kLnMaxQuads = 10;  // C <= 1280
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out16, int planes,
-                 long long plane_stride) {
+                 long long plane_stride, float* __restrict__ out32) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_LAYERNORM);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -455,11 +455,39 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
         y.y = (v[i].y - mean) * rstd * g.y + b.y;
         y.z = (v[i].z - mean) * rstd * g.z + b.z;
         y.w = (v[i].w - mean) * rstd * g.w + b.w;
-        store_split4(out16 + static_cast<size_t>(warp) * C + q * 4, plane_stride, planes, y);
+        if (out16) store_split4(out16 + static_cast<size_t>(warp) * C + q * 4, plane_stride, planes, y);
+        if (out32) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(warp) * C + q * 4) = y;
       }
     }
   }
   DFU_TR_END();
+}
+
+// =============================================================================================
+// ViT patch embedding operand: NCHW fp32 -> fp16 planes [B * (1 + nP)][C*P*P], one zero row (CLS slot) per sample.
+// One thread per 4 consecutive kx of an output row: a 16-byte read, an 8-byte write per plane.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int P, __half* __restrict__ out, int planes,
+                long long plane_stride) {
+  pdl_trigger();
+  pdl_wait();
+  const int gw = W / P, gh = H / P, K = C * P * P, K4 = K >> 2, rows = 1 + gw * gh;
+  const long long total = static_cast<long long>(B) * rows * K4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kq = static_cast<int>(i % K4);
+    const long long t = i / K4;
+    const int r = static_cast<int>(t % rows);
+    const int b = static_cast<int>(t / rows);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r > 0) {
+      const int k = kq * 4, c = k / (P * P), rem = k - c * P * P, ky = rem / P, kx = rem - ky * P;
+      const int py = (r - 1) / gw, px = (r - 1) - py * gw;
+      v = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * C + c) * H + py * P + ky) * W + px * P + kx);
+    }
+    store_split4(out + static_cast<size_t>(t) * K + kq * 4, plane_stride, planes, v);
+  }
 }
 
 // =============================================================================================
@@ -693,12 +721,22 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
   return DFU_OK;
 }
 
+int dfu_patchify_f16(const float* x, int B, int C, int H, int W, int P, void* out16, int planes, int64_t plane_stride,
+                     void* stream_) {
+  DFU_REQUIRE(x && out16 && P > 0 && P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "patchify: H=%d W=%d P=%d", H, W, P);
+  const long long total = static_cast<long long>(B) * (1 + (H / P) * (W / P)) * (C * P * P / 4);
+  DFU_CHECK_CUDA(launch_k(patchify_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream_), x, B, C, H, W, P, static_cast<__half*>(out16), planes, plane_stride));
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
 int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* out16,
-                  int planes, int64_t plane_stride, void* stream_) {
+                  int planes, int64_t plane_stride, float* out32, void* stream_) {
   DFU_REQUIRE(C % 4 == 0 && C / 4 <= 32 * kLnMaxQuads, "layernorm: C=%d unsupported", C);
+  DFU_REQUIRE(out16 || out32, "layernorm: no output");
   const int warps_per_block = 8;
   const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  DFU_CHECK_CUDA(launch_k(layernorm_kernel, dim3(blocks), dim3(warps_per_block * 32), 0, static_cast<cudaStream_t>(stream_), x, M, C, gamma, beta, eps, static_cast<__half*>(out16), planes, plane_stride));
+  DFU_CHECK_CUDA(launch_k(layernorm_kernel, dim3(blocks), dim3(warps_per_block * 32), 0, static_cast<cudaStream_t>(stream_), x, M, C, gamma, beta, eps, static_cast<__half*>(out16), planes, plane_stride, out32));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

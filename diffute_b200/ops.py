@@ -325,8 +325,9 @@ def gemm_stats():
 
 
 def set_epilogue(d: Gemm, *, out_f32=None, out_f16=None, bias=None, rowvec=None, rows_per_sample=0, residual=None,
-                 alpha: float = 1.0, geglu: bool = False):
+                 alpha: float = 1.0, geglu: bool = False, gelu: bool = False):
     d.alpha = alpha
+    d.act = 1 if gelu else 0
     d.bias = _ptr(bias)
     if rowvec is not None:
         d.rowvec = rowvec.data_ptr()
@@ -415,12 +416,22 @@ def groupnorm(src0: torch.Tensor, gamma, beta, eps: float, silu: bool, prec: int
                               buf.numel(), ws.sync[2:].data_ptr(), _stream()), "dfu_groupnorm")  # counters at sync[10:]
 
 
-def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: torch.Tensor):
-    """x [M, C] fp32 -> out16 [planes, M, C]."""
+def layernorm(x: torch.Tensor, gamma, beta, eps: float, out16: Optional[torch.Tensor] = None,
+              out32: Optional[torch.Tensor] = None):
+    """x [M, C] fp32 -> out16 [planes, M, C] fp16 operand planes and / or out32 [M, C] fp32."""
     M, C = x.shape
-    with _Prof('layernorm', 1, 0.0, float(M * C) * (4 + 2 * out16.shape[0])):
-        check(lib().dfu_layernorm(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
-                                  out16.shape[0], out16.stride(0), _stream()), "dfu_layernorm")
+    planes = out16.shape[0] if out16 is not None else 0
+    with _Prof('layernorm', 1, 0.0, float(M * C) * (4 + 2 * planes + (4 if out32 is not None else 0))):
+        check(lib().dfu_layernorm(x.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(out16), max(planes, 1),
+                                  out16.stride(0) if out16 is not None else 0, _ptr(out32), _stream()), "dfu_layernorm")
+
+
+def patchify_f16(x: torch.Tensor, patch: int, out16: torch.Tensor):
+    """x [B, C, H, W] fp32 NCHW -> out16 [planes, B*(1 + (H/P)*(W/P)), C*P*P] (row 0 of each sample = zeros, the CLS slot)."""
+    B, Cc, H, W = x.shape
+    with _Prof('patchify', 1):
+        check(lib().dfu_patchify_f16(x.data_ptr(), B, Cc, H, W, patch, out16.data_ptr(), out16.shape[0], out16.stride(0),
+                                     _stream()), "dfu_patchify_f16")
 
 
 CAST_PLAIN, CAST_UP2X, CAST_S2D = 0, 1, 2

@@ -81,6 +81,8 @@ typedef struct DfuGemm {
   int32_t B, H, W;         /* output grid when conv=1 */
   /* epilogue: v = alpha*acc + bias[n] + rowvec[(m / rows_per_sample), n] + residual[m, n] */
   int32_t epi;             /* DFU_EPI_* */
+  int32_t act;             /* 0: none; 1: exact-erf GELU applied to v before it is stored (DFU_EPI_F32 / DFU_EPI_F16):
+                              the non-gated MLP of the TrOCR ViT glyph encoder (app.ipynb:546-548, :773-776) */
   float alpha;
   const float* bias;       /* [n] or NULL (packed like the weights for GEGLU) */
   const float* rowvec;     /* [samples, rowvec_ld] or NULL (time-embedding add) */
@@ -132,9 +134,15 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
                   const float* gamma, const float* beta, float eps, int silu, void* out16, int planes,
                   int64_t plane_stride, float* out32, void* raw16, void* workspace, size_t workspace_bytes,
                   void* sync_words, void* stream);
-/* BasicTransformerBlock.norm1/2/3 (LayerNorm, eps 1e-5) over [M, C] tokens -> fp16 operand planes. */
+/* BasicTransformerBlock.norm1/2/3 (LayerNorm, eps 1e-5) over [M, C] tokens -> fp16 operand planes (out16) and / or an
+ * fp32 copy (out32: the ViT glyph encoder's final layernorm returns fp32 last_hidden_state). */
 int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* out16,
-                  int planes, int64_t plane_stride, void* stream);
+                  int planes, int64_t plane_stride, float* out32, void* stream);
+/* ViT patch embedding operand (TrOCR encoder, app.ipynb:773-776): NCHW fp32 pixel_values [B, C, H, W] ->
+ * fp16 planes [B * (1 + (H/P)*(W/P)), C*P*P], row 0 of every sample zero (the CLS slot: its embedding comes in through
+ * the GEMM's residual operand), row 1 + py*(W/P) + px = the patch flattened in (c, ky, kx) order = Conv2d's weight order. */
+int dfu_patchify_f16(const float* x, int B, int C, int H, int W, int P, void* out16, int planes, int64_t plane_stride,
+                     void* stream);
 /* fp32 NHWC -> fp16 operand. mode 0: as is; 1: nearest 2x upsample (Upsample2D's F.interpolate folded into the
  * operand of its conv); 2: space-to-depth parity planes [py*2+px][B][H/2][W/2][C] (Downsample2D stride-2 conv). */
 int dfu_cast_f16(const float* x, int B, int H, int W, int C, int mode, void* out16, int planes,
