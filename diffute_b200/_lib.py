@@ -31,6 +31,7 @@ class Gemm(C.Structure):
     _fields_ = [
         ("m", C.c_int32), ("n", C.c_int32), ("ngroups", C.c_int32), ("npass", C.c_int32),
         ("g", GemmOperand * 2),
+        ("batch", C.c_int32), ("a_batch_rows", C.c_int32), ("b_batch_rows", C.c_int32),
         ("conv", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("epi", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float),
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int32), ("rows_per_sample", C.c_int32),

@@ -69,10 +69,10 @@ __device__ __forceinline__ void reduce_quad(const float* __restrict__ ws, int sp
 // ---------------------------------------------------------------------------------------------
 template <int S>
 __device__ __forceinline__ void cluster_reduce(const GemmKernelParams& p, const uint8_t* smem, int split, int n_tile0,
-                                               int m0, int x0, int y0, int img0) {
+                                               int m0, int x0, int y0, int img0, int m_end) {
   // Only the rows the tile really has are reduced, split evenly over the S CTAs (a 64-pixel map fills half a tile: with
   // a fixed 128 / S rows per CTA half of the cluster would idle through the reduction).
-  const int tile_rows = p.conv ? p.bw * p.bh * p.bn : min(kBlockM, p.e.M - m0);
+  const int tile_rows = p.conv ? p.bw * p.bh * p.bn : min(kBlockM, m_end - m0);
   const int rows_per = (tile_rows + S - 1) / S;
   constexpr int CH = S < 8 ? S : 8;  // remote loads in flight per thread (registers: 16 in flight would spill)
   const bool geglu = p.e.epi == DFU_EPI_GEGLU;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void cluster_reduce(const GemmKernelParams& p, const 
       m = (img * p.H + y) * p.W + x;
     } else {
       m = m0 + rr;
-      valid = m < p.e.M;
+      valid = m < m_end;
     }
     if (!valid) continue;
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -183,7 +183,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int kb0 = static_cast<int>(static_cast<long long>(p.total_kb) * split / p.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(p.total_kb) * (split + 1) / p.splits);
   const int n_tile0 = tn * p.block_n;
-  int m0 = tm * kBlockM, x0 = 0, y0 = 0, img0 = 0;
+  int m0, a_row0, b_off, m_end, x0 = 0, y0 = 0, img0 = 0;
+  batch_coords(p.bt, tm, p.e.M, m0, a_row0, b_off, m_end);
   if (p.conv) {
     int t = tm;
     x0 = (t % p.tiles_x) * p.bw;
@@ -241,13 +242,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_arrive_expect_tx(&full_bar[stage], nplane * (p.a_tx_bytes[gi] + p.b_tx_bytes));
           for (uint32_t pl = 0; pl < nplane; ++pl)
             tma_load_2d(sB + pl * b_bytes, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK,
-                        n_tile0 + static_cast<int>(pl) * G.b_plane);
+                        n_tile0 + b_off + static_cast<int>(pl) * G.b_plane);
         }
         if (load_a) {
           for (uint32_t pl = 0; pl < nplane; ++pl) {
             const int a_sel = static_cast<int>(pl) * G.a_plane;
             if (G.a_mode == 0) {
-              tma_load_2d(sA + pl * kABytes, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
+              tma_load_2d(sA + pl * kABytes, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, a_row0 + a_sel);
             } else {
               tma_load_4d(sA + pl * kABytes, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
                           img0 + G.dn[tap] + a_sel);
@@ -333,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       m = (img * p.H + y) * p.W + x;
     } else {
       m = m0 + r;
-      valid = m < p.e.M;
+      valid = m < m_end;
     }
     // ---- everything that does not need the accumulator happens while the main loop runs ----
     const bool direct = p.splits == 1;
@@ -508,10 +509,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     cluster_sync_all();
     if (warp >= 2) {
       switch (p.cluster) {
-        case 2: cluster_reduce<2>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
-        case 4: cluster_reduce<4>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
-        case 8: cluster_reduce<8>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
-        default: cluster_reduce<16>(p, smem, split, n_tile0, m0, x0, y0, img0); break;
+        case 2: cluster_reduce<2>(p, smem, split, n_tile0, m0, x0, y0, img0, m_end); break;
+        case 4: cluster_reduce<4>(p, smem, split, n_tile0, m0, x0, y0, img0, m_end); break;
+        case 8: cluster_reduce<8>(p, smem, split, n_tile0, m0, x0, y0, img0, m_end); break;
+        default: cluster_reduce<16>(p, smem, split, n_tile0, m0, x0, y0, img0, m_end); break;
       }
     }
     cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
@@ -524,6 +525,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+}
+
+// Small outputs (the deep UNet levels: 64..256 rows x 1280 columns, 10-20 slices): one thread per quad walks its slices in
+// ~5 dependent rounds of L2 latency on a nearly empty GPU (4.5 us for 6.5 MB, measured).  Here T = 2/4/8 lanes share a
+// quad: lane j loads slices j, j+T, ... (all in flight at once), adds them in slice order and the T partial sums are
+// combined by a fixed xor-shuffle tree — one L2 round trip instead of five, still bit-identical run to run.
+template <int T>
+__device__ __forceinline__ float4 sum_partials_team(const float* __restrict__ src, size_t plane, int splits, int sub) {
+  constexpr int kMaxPer = 8;
+  float4 t[kMaxPer];
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) {
+    const int sl = sub + i * T;
+    t[i] = (sl < splits) ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(sl) * plane))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 v = t[0];
+#pragma unroll
+  for (int i = 1; i < kMaxPer; ++i) {
+    v.x += t[i].x; v.y += t[i].y; v.z += t[i].z; v.w += t[i].w;
+  }
+#pragma unroll
+  for (int o = T >> 1; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  return v;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) splitk_reduce_team_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
+  pdl_trigger();
+  DFU_TR_BEGIN(TR_SPLITK_REDUCE);
+  pdl_wait();
+  DFU_TR_MARK(6);
+  const bool geglu = e.epi == DFU_EPI_GEGLU;
+  const int qpr = geglu ? e.N / 8 : e.N / 4;
+  const size_t plane = static_cast<size_t>(e.M) * e.N;
+  const long long total = static_cast<long long>(e.M) * qpr;            // quads; T consecutive lanes per quad
+  const long long teams = (static_cast<long long>(gridDim.x) * blockDim.x) / T;
+  const int sub = threadIdx.x % T;
+  for (long long idx = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / T; idx - (idx % (32 / T)) < total;
+       idx += teams) {  // (whole warps iterate together: the shuffles need every lane)
+    const bool live = idx < total;
+    const long long id = live ? idx : total - 1;
+    const int m = static_cast<int>(id / qpr);
+    const int qi = static_cast<int>(id % qpr);
+    if (geglu) {
+      const int n_a = (qi >> 2) * 32 + (qi & 3) * 4;
+      const float* src = ws + static_cast<size_t>(m) * e.N + n_a;
+      const float4 a = sum_partials_team<T>(src, plane, splits, sub);
+      const float4 g = sum_partials_team<T>(src + 16, plane, splits, sub);
+      if (live && sub == 0) epi_geglu_quad(e, m, n_a, a, g);
+    } else {
+      const int n = qi * 4;
+      const float4 v = sum_partials_team<T>(ws + static_cast<size_t>(m) * e.N + n, plane, splits, sub);
+      if (live && sub == 0) epi_quad(e, m, n, v);
+    }
+  }
+  DFU_TR_END();
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, EpiParams e) {
@@ -584,6 +647,10 @@ int plan_gemm(const DfuGemm* d, Plan* pl) {
   } else {
     pl->bw = pl->bh = pl->bn = pl->tiles_x = pl->tiles_y = 0;
     pl->tiles_m = (d->m + kBlockM - 1) / kBlockM;
+    if (d->batch > 1) {
+      DFU_REQUIRE(d->m % d->batch == 0 && d->ngroups == 1 && d->g[0].a_mode == 0, "gemm: batch=%d needs one matrix operand group and m %% batch == 0", d->batch);
+      pl->tiles_m = d->batch * ((d->m / d->batch + kBlockM - 1) / kBlockM);
+    }
   }
   const int sms = num_sms() > 0 ? num_sms() : 148;
   DFU_REQUIRE(d->kernel >= 0 && d->kernel <= 2, "gemm: kernel=%d (0 auto, 1 tile-per-CTA, 2 persistent pairs)", d->kernel);
@@ -736,6 +803,18 @@ void fill_group_dev(const DfuGemmOperand& o, GroupDev& G) {
   }
 }
 
+void fill_batch_dev(const DfuGemm* d, BatchDev& bt) {
+  bt.tiles_per_batch = 0;
+  bt.rows_per_batch = d->m;
+  bt.a_batch_rows = bt.b_batch_rows = 0;
+  if (d->batch > 1 && !d->conv) {
+    bt.rows_per_batch = d->m / d->batch;
+    bt.tiles_per_batch = (bt.rows_per_batch + kBlockM - 1) / kBlockM;
+    bt.a_batch_rows = d->a_batch_rows;
+    bt.b_batch_rows = d->b_batch_rows;
+  }
+}
+
 void fill_epi_params(const DfuGemm* d, EpiParams& e) {
   e.M = d->m;
   e.N = d->n;
@@ -813,6 +892,7 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   p.tiles_x = pl.tiles_x;
   p.tiles_y = pl.tiles_y;
   p.b_tx_bytes = static_cast<uint32_t>(pl.block_n) * kBlockK * 2;
+  fill_batch_dev(d, p.bt);
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(pl.block_n)) cols <<= 1;
   p.tmem_cols = cols;
@@ -848,6 +928,16 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
     long long blocks = (total + 255) / 256;
     const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
     if (blocks > cap) blocks = cap;
+    // few quads (deep levels): several lanes per quad so that all slices of a quad are in flight at once
+    int team = 1;
+    while (team < 8 && total * team * 2 <= cap * 256 && team * 2 <= pl.splits && (pl.splits + team * 2 - 1) / (team * 2) >= 2) team *= 2;
+    if (team > 1 && (pl.splits + team - 1) / team <= 8) {
+      const long long tb = (total * team + 255) / 256;
+      if (team == 2) DFU_CHECK_CUDA(launch_k(splitk_reduce_team_kernel<2>, dim3(static_cast<unsigned>(tb)), dim3(256), 0, stream, p.ws, pl.splits, e));
+      else if (team == 4) DFU_CHECK_CUDA(launch_k(splitk_reduce_team_kernel<4>, dim3(static_cast<unsigned>(tb)), dim3(256), 0, stream, p.ws, pl.splits, e));
+      else DFU_CHECK_CUDA(launch_k(splitk_reduce_team_kernel<8>, dim3(static_cast<unsigned>(tb)), dim3(256), 0, stream, p.ws, pl.splits, e));
+      return DFU_OK;
+    }
     DFU_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p.ws, pl.splits, e));
   }
   return DFU_OK;

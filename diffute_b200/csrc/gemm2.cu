@@ -34,6 +34,7 @@ struct Gemm2Params {
   uint32_t a_tx_bytes[2];
   uint32_t b_tx_bytes;  // per CTA
   uint32_t tmem_cols;   // allocated columns (power of two >= 2 * block_n); accumulator s starts at s * tmem_cols / 2
+  BatchDev bt;
   int debug;            // experiments only (DFU_G2_DEBUG): bit 0 = every CTA signals its OWN full barrier (results of the
                         // peer half are then unsynchronised: timing only)
   EpiParams e;
@@ -98,11 +99,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (threadIdx.x == 0) DFU_TR_SHARED_MARK(5);
 
   // tile -> coordinates of THIS CTA's 128 rows
+  int a_row0 = 0, b_off = 0, m_end = 0;  // (batched products: A / B row bases and the end of the batch's output rows)
   auto tile_coords = [&](int tile, int& n_tile0, int& m0, int& x0, int& y0, int& img0) {
     const int tn = tile % p.tiles_n;
     const int tm = 2 * (tile / p.tiles_n) + static_cast<int>(rank);
     n_tile0 = tn * p.block_n;
-    m0 = tm * kBlockM;
+    batch_coords(p.bt, tm, p.e.M, m0, a_row0, b_off, m_end);
+    if (tm >= p.tiles_m) m_end = m0;  // the empty peer tile of an odd last pair
     x0 = y0 = img0 = 0;
     if (p.conv) {
       int t = tm;
@@ -147,13 +150,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           if (load_b) {
             for (uint32_t pl = 0; pl < nplane; ++pl)
               tma_load_2d_cg2(sB + pl * b_bytes, mB, bar, (tap * G.nchunks + chunk) * kBlockK,
-                              n_tile0 + static_cast<int>(rank) * (p.block_n >> 1) + static_cast<int>(pl) * G.b_plane);
+                              n_tile0 + b_off + static_cast<int>(rank) * (p.block_n >> 1) + static_cast<int>(pl) * G.b_plane);
           }
           if (load_a) {
             for (uint32_t pl = 0; pl < nplane; ++pl) {
               const int a_sel = static_cast<int>(pl) * G.a_plane;
               if (G.a_mode == 0) {
-                tma_load_2d_cg2(sA + pl * kABytes, mA, bar, (tap * G.nchunks + chunk) * kBlockK, m0 + a_sel);
+                tma_load_2d_cg2(sA + pl * kABytes, mA, bar, (tap * G.nchunks + chunk) * kBlockK, a_row0 + a_sel);
               } else {
                 tma_load_4d_cg2(sA + pl * kABytes, mA, bar, chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
                                 img0 + G.dn[tap] + a_sel);
@@ -271,7 +274,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         m = (img * p.H + y) * p.W + x;
       } else {
         m = m0 + r;
-        valid = m < e.M;
+        valid = m < m_end;
       }
       // (m, valid) of the rows this lane stores after the transpose through shared memory
       const int vmask = valid ? 1 : 0;
@@ -448,6 +451,7 @@ int run_gemm2(const DfuGemm* d, const Plan& pl, cudaStream_t stream) {
   while (cols < 2u * static_cast<uint32_t>(pl.block_n)) cols <<= 1;
   p.tmem_cols = cols;
   fill_epi_params(d, p.e);
+  fill_batch_dev(d, p.bt);
   static const int debug = getenv("DFU_G2_DEBUG") ? atoi(getenv("DFU_G2_DEBUG")) : 0;
   p.debug = debug;
   if (first_use_on_device(ONCE_GEMM2_ATTR))

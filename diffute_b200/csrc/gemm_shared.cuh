@@ -20,6 +20,27 @@ struct GroupDev {
   int8_t dn[9], dy[9], dx[9];
 };
 
+// batched matrix products (DfuGemm.batch > 1): 128-row m-tiles never straddle two batches
+struct BatchDev {
+  int tiles_per_batch;  // 0: not batched
+  int rows_per_batch;   // m / batch (output rows of one product)
+  int a_batch_rows, b_batch_rows;
+};
+// m-tile index -> first output row, first A row, B row offset, end of the valid output rows
+__device__ __forceinline__ void batch_coords(const BatchDev& bt, int tm, int M, int& m0, int& a_row0, int& b_off, int& m_end) {
+  if (bt.tiles_per_batch > 0) {
+    const int b = tm / bt.tiles_per_batch, ti = tm - b * bt.tiles_per_batch;
+    m0 = b * bt.rows_per_batch + ti * 128;
+    a_row0 = b * bt.a_batch_rows + ti * 128;
+    b_off = b * bt.b_batch_rows;
+    m_end = (b + 1) * bt.rows_per_batch;
+  } else {
+    m0 = a_row0 = tm * 128;
+    b_off = 0;
+    m_end = M;
+  }
+}
+
 struct EpiParams {
   int M, N;
   int epi;
@@ -47,6 +68,7 @@ struct GemmKernelParams {
   uint32_t b_tx_bytes;
   uint32_t tmem_cols;
   float* ws;
+  BatchDev bt;
   int cluster;         // > 1: the `splits` K-slices of a tile form a thread-block cluster and reduce through DSMEM
   unsigned int* sync;  // grid-barrier words (zero between launches); non-null => fused split-K second stage
   EpiParams e;
@@ -150,6 +172,7 @@ int plan_gemm(const DfuGemm* d, Plan* pl);
 int encode_group(const DfuGemm* d, const DfuGemmOperand& o, const Plan& pl, int b_box_rows, CUtensorMap* mA,
                  CUtensorMap* mB, uint32_t* a_tx);
 void fill_epi_params(const DfuGemm* d, EpiParams& e);
+void fill_batch_dev(const DfuGemm* d, BatchDev& bt);
 void fill_group_dev(const DfuGemmOperand& o, GroupDev& G);
 int run_gemm2(const DfuGemm* d, const Plan& pl, cudaStream_t stream);  // gemm2.cu
 

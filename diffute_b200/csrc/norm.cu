@@ -399,6 +399,10 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnApply a, int U, int q
 // =============================================================================================
 constexpr int kLnMaxQuads = 10;  // C <= 1280
 
+// QPL = float4 per lane per token (3: C <= 384, 5: C <= 640, 10: C <= 1280) keeps the register count proportional to the
+// row length (64 resident warps per SM for the 320-wide level); TOK = tokens per warp, loaded together: at batch 8 the
+// kernel is bandwidth-bound and needs the bytes in flight, at batch 1 it is latency-bound and TOK = 1 keeps the grid wide.
+template <int QPL, int TOK>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out16, int planes,
@@ -411,7 +415,7 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
   // gamma / beta are weights (they stream from HBM every step): copy them to shared memory BEFORE waiting for the
   // producer kernel, so that their latency overlaps its tail instead of sitting on the critical path after the
   // reductions (shared memory, not registers: 80 more live registers would halve the occupancy)
-  __shared__ __align__(16) float s_g[kLnMaxQuads * 128], s_b[kLnMaxQuads * 128];
+  __shared__ __align__(16) float s_g[QPL * 128], s_b[QPL * 128];
   for (int qd = threadIdx.x; qd < C4; qd += blockDim.x) {
     reinterpret_cast<float4*>(s_g)[qd] = __ldg(reinterpret_cast<const float4*>(gamma) + qd);
     reinterpret_cast<float4*>(s_b)[qd] = __ldg(reinterpret_cast<const float4*>(beta) + qd);
@@ -419,44 +423,51 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
   __syncthreads();
   pdl_wait();
   DFU_TR_MARK(6);
-  if (warp < M) {
-    const float4* row = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
-    float4 v[kLnMaxQuads];
+  const int tok0 = warp * TOK;
+  float4 v[TOK][QPL];
+#pragma unroll
+  for (int t = 0; t < TOK; ++t) {
+    const float4* row = reinterpret_cast<const float4*>(x + static_cast<size_t>(tok0 + t) * C);
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) {
+      const int q = lane + 32 * i;
+      if (tok0 + t < M && q < C4) v[t][i] = row[q];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TOK; ++t) {
+    if (tok0 + t >= M) break;  // (warp-uniform)
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxQuads; ++i) {
+    for (int i = 0; i < QPL; ++i) {
       const int q = lane + 32 * i;
-      if (q < C4) v[i] = row[q];
-    }
-#pragma unroll
-    for (int i = 0; i < kLnMaxQuads; ++i) {
-      const int q = lane + 32 * i;
-      if (q < C4) s += v[i].x + v[i].y + v[i].z + v[i].w;
+      if (q < C4) s += v[t][i].x + v[t][i].y + v[t][i].z + v[t][i].w;
     }
     const float mean = warp_sum(s) / C;
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxQuads; ++i) {
+    for (int i = 0; i < QPL; ++i) {
       const int q = lane + 32 * i;
       if (q < C4) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        const float a = v[t][i].x - mean, b = v[t][i].y - mean, c = v[t][i].z - mean, d = v[t][i].w - mean;
         ss += a * a + b * b + c * c + d * d;
       }
     }
     const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+    const size_t base = static_cast<size_t>(tok0 + t) * C;
 #pragma unroll
-    for (int i = 0; i < kLnMaxQuads; ++i) {
+    for (int i = 0; i < QPL; ++i) {
       const int q = lane + 32 * i;
       if (q < C4) {
         const float4 g = reinterpret_cast<const float4*>(s_g)[q];
         const float4 b = reinterpret_cast<const float4*>(s_b)[q];
         float4 y;
-        y.x = (v[i].x - mean) * rstd * g.x + b.x;
-        y.y = (v[i].y - mean) * rstd * g.y + b.y;
-        y.z = (v[i].z - mean) * rstd * g.z + b.z;
-        y.w = (v[i].w - mean) * rstd * g.w + b.w;
-        if (out16) store_split4(out16 + static_cast<size_t>(warp) * C + q * 4, plane_stride, planes, y);
-        if (out32) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(warp) * C + q * 4) = y;
+        y.x = (v[t][i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[t][i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[t][i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[t][i].w - mean) * rstd * g.w + b.w;
+        if (out16) store_split4(out16 + base + q * 4, plane_stride, planes, y);
+        if (out32) *reinterpret_cast<float4*>(out32 + base + q * 4) = y;
       }
     }
   }
@@ -735,8 +746,20 @@ int dfu_layernorm(const float* x, int M, int C, const float* gamma, const float*
   DFU_REQUIRE(C % 4 == 0 && C / 4 <= 32 * kLnMaxQuads, "layernorm: C=%d unsupported", C);
   DFU_REQUIRE(out16 || out32, "layernorm: no output");
   const int warps_per_block = 8;
-  const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  DFU_CHECK_CUDA(launch_k(layernorm_kernel, dim3(blocks), dim3(warps_per_block * 32), 0, static_cast<cudaStream_t>(stream_), x, M, C, gamma, beta, eps, static_cast<__half*>(out16), planes, plane_stride, out32));
+  // two tokens per warp once the grid is several waves deep (batched levels: bandwidth-bound, wants bytes in flight)
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const int tok = (M >= sms * 8 * 8) ? 2 : 1;
+  const int blocks = (M + warps_per_block * tok - 1) / (warps_per_block * tok);
+  const int qpl = C / 4 <= 96 ? 3 : (C / 4 <= 160 ? 5 : 10);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  __half* o16 = static_cast<__half*>(out16);
+#define DFU_LN_LAUNCH(Q, T) launch_k(layernorm_kernel<Q, T>, dim3(blocks), dim3(warps_per_block * 32), 0, st, x, M, C, gamma, beta, eps, o16, planes, plane_stride, out32)
+  cudaError_t e;
+  if (qpl == 3) e = tok == 2 ? DFU_LN_LAUNCH(3, 2) : DFU_LN_LAUNCH(3, 1);
+  else if (qpl == 5) e = tok == 2 ? DFU_LN_LAUNCH(5, 2) : DFU_LN_LAUNCH(5, 1);
+  else e = tok == 2 ? DFU_LN_LAUNCH(10, 2) : DFU_LN_LAUNCH(10, 1);
+#undef DFU_LN_LAUNCH
+  DFU_CHECK_CUDA(e);
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -292,7 +292,7 @@ if os.path.exists(TUNE_PATH):
 
 def gemm_key(d: Gemm) -> str:
     kb = sum(d.g[i].ntaps * (d.g[i].k_per_tap // 64) for i in range(d.ngroups)) * d.npass
-    return f"{d.conv}:{d.m}:{d.n}:{kb}:{d.epi}"
+    return f"{d.conv}:{d.m}:{d.n}:{kb}:{d.epi}" + (f":b{d.batch}" if d.batch > 1 else "")
 
 
 def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
@@ -355,11 +355,16 @@ def _set_tune(d: Gemm, tune):
 
 
 def linear(a16: torch.Tensor, w16: torch.Tensor, n: int, prec: int, *, tune: Tuple[int, ...] = (0, 0, 0),
-           ws: Optional[Workspace] = None, **epi):
-    """a16 [planes, M, K] fp16 operand; w16 packed [planes*n, K]; epilogue kwargs as set_epilogue."""
+           ws: Optional[Workspace] = None, batch: int = 0, a_batch_rows: int = 0, b_batch_rows: int = 0, **epi):
+    """a16 [planes, M, K] fp16 operand; w16 packed [planes*n, K]; epilogue kwargs as set_epilogue.
+
+    batch > 1: M = batch * m_b rows hold `batch` independent products; product b multiplies A rows
+    [b*a_batch_rows, b*a_batch_rows + m_b) with B rows [b*b_batch_rows, b*b_batch_rows + n) (B then is an activation
+    view [planes, rows, K]) and writes output rows [b*m_b, (b+1)*m_b)."""
     planes = planes_of(prec)
     d = Gemm()
     d.m, d.n = a16.shape[1], n
+    d.batch, d.a_batch_rows, d.b_batch_rows = batch, a_batch_rows, b_batch_rows
     d.ngroups, d.npass = 1, npass_of(prec)
     matrix_operand(d.g[0], a16, w16, a16.shape[2], planes)
     set_epilogue(d, **epi)

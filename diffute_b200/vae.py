@@ -230,7 +230,7 @@ class AutoencoderKL:
 
     def _attention(self, k, x):
         """Single-head d=C spatial self-attention: S = Q K^T on the contraction core, fp32 row softmax,
-        O = P V with V transposed once; per sample (N = H*W keys)."""
+        O = P V with V transposed once; all samples of the batch in one launch per stage (N = H*W keys per sample)."""
         w, prec, P = self.w, self.prec, self.planes
         B, H, W, C = x.shape
         N = H * W
@@ -239,19 +239,18 @@ class AutoencoderKL:
                       out16=g16.view(P, B, H, W, C), ws=self.ws)
         qkv = self._op16("qkv", (B * N, 3 * C))
         ops.linear(g16, w[k + ".qkv.w16"], 3 * C, prec, ws=self.ws, out_f16=qkv, bias=w[k + ".qkv.b"])
-        s = self.arena.get("att.s", (N, N))
-        p16 = self._op16("att.p", (N, N))
-        vt = self._op16("att.vt", (C, N))
+        # every sample's S = Q K^T, row softmax and O = P V in ONE batched launch each (no per-sample host loop):
+        # product b reads rows [b*N, (b+1)*N) of the fused q|k|v matrix; V is transposed once per sample into [C, N]
+        s = self.arena.get("att.s", (B * N, N))
+        p16 = self._op16("att.p", (B * N, N))
+        vt = self._op16("att.vt", (B * C, N))
         o16 = self._op16("att.o", (B * N, C))
-        for b in range(B):
-            rows = slice(b * N, (b + 1) * N)
-            q = qkv[:, rows, 0:C]
-            kk = qkv[:, rows, C:2 * C]
-            v = qkv[:, rows, 2 * C:3 * C]
-            ops.linear(q, kk, N, prec, ws=self.ws, out_f32=s)           # S = Q K^T (K rows act as the "weights")
-            ops.softmax_rows(s, C ** -0.5, p16)
-            ops.transpose_f16(v, vt)
-            ops.linear(p16, vt, C, prec, ws=self.ws, out_f16=o16[:, rows, :])
+        q, kk, v = qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:3 * C]
+        ops.linear(q, kk, N, prec, ws=self.ws, batch=B, a_batch_rows=N, b_batch_rows=N, out_f32=s)
+        ops.softmax_rows(s, C ** -0.5, p16)
+        for pl in range(P):
+            ops.transpose_f16(v[pl].view(B, N, C), vt[pl].view(B, C, N))
+        ops.linear(p16, vt, C, prec, ws=self.ws, batch=B, a_batch_rows=N, b_batch_rows=C, out_f16=o16)
         out = self._fp32([x], (B, H, W, C))
         ops.linear(o16, w[k + ".to_out.0.w16"], C, prec, ws=self.ws, out_f32=out.view(-1, C),
                    bias=w[k + ".to_out.0.bias"], residual=x.view(-1, C))

@@ -77,6 +77,11 @@ typedef struct DfuGemm {
   int32_t ngroups;         /* 1 or 2 */
   int32_t npass;           /* 1 (DFU_PREC_FP16) or 3 (DFU_PREC_FP16X2) */
   DfuGemmOperand g[2];
+  int32_t batch;           /* 0/1: one problem.  > 1: `batch` independent products of m / batch rows each (matrix operands,
+                              one group): batch b uses A rows [b*a_batch_rows, ...), B rows [b*b_batch_rows, ...) and
+                              writes output / residual rows [b*m/batch, (b+1)*m/batch) — the per-sample Q K^T and P V of the
+                              VAE's single-head attention in ONE launch */
+  int32_t a_batch_rows, b_batch_rows;
   int32_t conv;            /* 1: rows are output pixels of a [B,H,W] grid (mode-1 operands) */
   int32_t B, H, W;         /* output grid when conv=1 */
   /* epilogue: v = alpha*acc + bias[n] + rowvec[(m / rows_per_sample), n] + residual[m, n] */

@@ -1,6 +1,6 @@
 """GroupNorm variants timed with the in-kernel tracer (diagnostic library): cluster shapes (DFU_GN_FORCE=S,T) against
 the two-launch path (DFU_GN_CLUSTER=0 needs a fresh process, so it is selected with argv).
-  DFU_TRACE=1 python scripts/bench_gn.py [H W C]"""
+  DFU_TRACE=1 python scripts/bench_gn.py [H W C [B]]"""
 import os, sys
 os.environ["DFU_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,9 +8,11 @@ import torch
 from diffute_b200 import ops, trace
 
 H, W, C = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (64, 64, 320)
-x = torch.randn(1, H, W, C, device="cuda")
+B = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+x = torch.randn(B, H, W, C, device="cuda")
 g = torch.ones(C, device="cuda"); b = torch.zeros(C, device="cuda")
-out = torch.empty(1, 1, H, W, C, dtype=torch.float16, device="cuda")
+out = torch.empty(1, B, H, W, C, dtype=torch.float16, device="cuda")
+print(f"GroupNorm B={B} {H}x{W}x{C}: {B * H * W * C * 6 / 1e6:.1f} MB algorithmic (4 B read + 2 B write per element)")
 w = torch.randn(1 << 20, device="cuda")
 trace.enable(1 << 16)
 

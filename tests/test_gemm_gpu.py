@@ -207,3 +207,28 @@ def test_conv_with_fused_shortcut_and_residual(ops, prec):
         torch.cuda.synchronize()
         err = ((out.view(B, H, W, Cout).double() - ref).abs().max() / ref.abs().max()).item()
         assert err < ACC_TOL, (tune, err)
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("tune", [(0, 0, 0), (64, 2, 3), (128, 5, 2), (128, 1, 0, 2), (256, 1, 0, 2)])
+def test_batched_products(ops, prec, tune):
+    """DfuGemm.batch: independent products in one launch (per-sample Q K^T of the VAE attention): ragged rows per batch
+    (200 = one full + one partial 128-row tile), B operand an activation view with its own batch stride, both kernels,
+    cluster and workspace split-K."""
+    planes = ops.planes_of(prec)
+    nb, mb, n, K = 3, 200, 256, 192
+    a = _rand((nb * mb, K), 41)
+    b = _rand((nb * 300, K), 42, K ** -0.5)        # 300 rows per batch, only the first n = 256 are used
+    res = _rand((nb * mb, n), 43)
+    a16 = ops.split_f16(a, planes)
+    b16 = ops.split_f16(b, planes)                  # [planes, nb*300, K] activation-style B
+    out = torch.full((nb * mb, n), float("nan"), device="cuda")
+    ops.linear(a16, b16, n, prec, tune=tune, batch=nb, a_batch_rows=mb, b_batch_rows=300, out_f32=out, residual=res)
+    torch.cuda.synchronize()
+    ar, br = _recombine(a16), _recombine(b16)
+    ref = torch.cat([ar[i * mb:(i + 1) * mb] @ br[i * 300:i * 300 + n].T for i in range(nb)], 0) + res.double()
+    if prec == 2:
+        ref = ref - torch.cat([a16[1, i * mb:(i + 1) * mb].double() @ b16[1, i * 300:i * 300 + n].double().T
+                               for i in range(nb)], 0)
+    err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < ACC_TOL, err
