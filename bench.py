@@ -212,6 +212,35 @@ def _event_ms(fn, n):
     return e0.elapsed_time(e1) / n
 
 
+def in_graph_class_ms(pipe, B, h, w, classes=("gemm", "attention", "groupnorm", "layernorm"), reps=20):
+    """In-graph cost of each kernel class of one UNet step by ablation: the step is re-captured with that class's
+    launches removed (same buffers, same order, PDL edges intact) and replayed; cost = full - ablated (CUDA events on the
+    replay stream, no per-launch event overhead).  Returns (full_ms, {class: ms})."""
+    import torch
+    from diffute_b200 import ops
+    A = pipe.unet.arena
+    srcs = [A.get("pipe.latents", (B, 4, h, w)), A.get("pipe.mask", (B, 1, h, w)), A.get("pipe.masked", (B, 4, h, w))]
+    t = A.get("pipe.state", (B + 2,))[:B]
+    real_lib = ops.lib
+
+    def graph_ms(ablate):
+        if ablate:
+            ops.lib = lambda: _AblatingLib(real_lib(), ablate)
+        try:
+            pipe.unet._forward_impl(B, h, w, srcs=srcs, t=t)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                pipe.unet._forward_impl(B, h, w, srcs=srcs, t=t)
+        finally:
+            ops.lib = real_lib
+        gr.replay()
+        return _event_ms(gr.replay, reps)
+
+    full = graph_ms(())
+    return full, {c: max(full - graph_ms((c,)), 0.0) for c in classes}
+
+
 def extra_configs(pipe, dev, peaks):
     """BASELINE configs 3 (1-GPU leg: batch 8), 4 (VAE encode+decode, batch 32) and 5 (768x768, batch 4, CFG x2), each
     with its own roofline sub-record.  Inputs are resident in HBM; CUDA events on the launch stream; one warm-up call,
@@ -236,12 +265,22 @@ def extra_configs(pipe, dev, peaks):
     graph.replay()
     step_ms = _event_ms(graph.replay, 10)
     step_tf = (UNET_GFLOP - UNET_CTX_GFLOP) * B / 1e3 / (step_ms / 1e3)
+    _, cls8 = in_graph_class_ms(pipe, B, PX // 8, PX // 8, reps=5)
+    gemm_gf = (UNET_GFLOP - UNET_CTX_GFLOP - 149.15) * B          # conv + linear FLOP of a step (attention cores excluded)
+    gemm_tf = gemm_gf / 1e3 / (cls8["gemm"] / 1e3) if cls8["gemm"] > 0 else 0.0
+    attn_tf = 149.15 * B / 1e3 / (cls8["attention"] / 1e3) if cls8["attention"] > 0 else 0.0
     out["config3_b8_1gpu"] = {
         "workload": "512x512, 50 DDIM steps, batch 8 on ONE GPU (BASELINE config 3, single-GPU leg)",
         "images_per_s": B / (ms / 1e3), "ms_per_batch": ms, "unet_step_ms": step_ms,
         "roofline": {"bound": "tensor", "achieved": step_tf, "peak": tf, "unit": "TFLOP/s", "frac": step_tf / tf,
                      "what": "whole UNet step at B=8 (all kernels): algorithmic FLOP / graph-replay time",
-                     "per_layer_roofline_ms": 4.411, "frac_of_per_layer_roofline": 4.411 / step_ms}}
+                     "per_layer_roofline_ms": 4.411, "frac_of_per_layer_roofline": 4.411 / step_ms},
+        "in_graph_ms_per_unet_step": {k: round(v, 3) for k, v in cls8.items()},
+        "roofline_gemm": {"kernel": "gemm_tc_kernel / gemm2_kernel at batch 8", "bound": "tensor", "achieved": gemm_tf,
+                          "peak": tf, "unit": "TFLOP/s", "frac": gemm_tf / tf,
+                          "what": "conv + linear FLOP of one step / in-graph duration of the contraction kernels"},
+        "roofline_attention": {"kernel": "attn_fwd_kernel at batch 8", "bound": "tensor", "achieved": attn_tf, "peak": tf,
+                               "unit": "TFLOP/s", "frac": attn_tf / tf}}
     del d
 
     # ---- config 4: AutoencoderKL encode + decode, 512x512, batch 32 -------------------------------------------
@@ -410,43 +449,19 @@ def run_gpu(args):
     # In-graph cost of each kernel class by ablation: replay the captured step with that class's launches removed
     # (same buffers, same order, PDL edges intact) and take the difference — CUDA events on the replay stream, no
     # per-launch event overhead.  This is the duration used for the roofline.
-    real_lib = ops.lib
-
-    def graph_ms(ablate):
-        if ablate:
-            ops.lib = lambda: _AblatingLib(real_lib(), ablate)
-        try:
-            pipe.unet._forward_impl(B, h, w, srcs=srcs, t=state[:B])
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                pipe.unet._forward_impl(B, h, w, srcs=srcs, t=state[:B])
-        finally:
-            ops.lib = real_lib
-        gr.replay()
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(20):
-            gr.replay()
-        a1.record()
-        torch.cuda.synchronize()
-        return a0.elapsed_time(a1) / 20
-
-    full_ms = graph_ms(())
-    in_graph = {c: max(full_ms - graph_ms((c,)), 0.0) for c in ("gemm", "attention", "groupnorm", "layernorm")}
+    full_ms, in_graph = in_graph_class_ms(pipe, B, h, w)
     g_ms = in_graph["gemm"] if in_graph["gemm"] > 0 else g_ms_events
     achieved = (g_gf / 1e3) / (g_ms / 1e3) if g_ms > 0 else 0.0  # TFLOP/s
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")  # ncu DRAM pass over one eager UNet step (B=1)
     if os.path.exists(tp) and B == 1:
         with open(tp) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_total"] / tj["gemm_launches_per_unet_step"]  # bytes per launch (ncu capture)
+            traffic = json.load(f)["dram_bytes_per_launch"]
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv + linear)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": traffic, "traffic_note": "avg DRAM bytes per gemm launch over one UNet step (ncu, cold L2): "
-                "2.15 GB per step = 1.73 GB of fp16 weights streamed once + operand reads; writes stay in L2",
+                "traffic": traffic, "traffic_note": "avg DRAM bytes per gemm launch over one UNet step (ncu, cold L2; "
+                "profiles/gemm_dram_r02.csv): 2.19 GB per step = 1.73 GB of fp16 weights streamed once + operand reads; "
+                "writes stay in L2",
                 "peak_source": peaks["src"], "launches_per_unet_step": g_n,
                 "avg_launch_us": (g_ms * 1e3 / g_n) if g_n else None,
                 "algorithmic_gflop_per_unet_step": g_gf, "tensor_passes": passes,

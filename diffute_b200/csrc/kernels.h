@@ -38,7 +38,7 @@ int num_sms();  // of the CURRENT device (cached per device)
 
 // true the first time it is called for (slot, current device): guards per-device one-time setup such as
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which a second device in the same process needs again
-enum : int { ONCE_GEMM_ATTR = 0, ONCE_ATTN_ATTR, ONCE_GEMV_ATTR, ONCE_CONV_OUT_ATTR, ONCE_GEMM2_ATTR, kOnceSlots = 8 };
+enum : int { ONCE_GEMM_ATTR = 0, ONCE_ATTN_ATTR, ONCE_GEMV_ATTR, ONCE_CONV_OUT_ATTR, ONCE_GEMM2_ATTR, ONCE_GN_SMEM_ATTR, kOnceSlots = 8 };
 bool first_use_on_device(int slot);
 
 // 1 unless DFU_PDL=0: launch with the programmatic-stream-serialization attribute (kernels call pdl_wait()).

@@ -395,6 +395,146 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnApply a, int U, int q
 }
 
 // =============================================================================================
+// Cluster GroupNorm with the slab staged in SHARED memory (cp.async, 16 bytes per request, no register cost): the same
+// one-launch / one-read scheme as gn_cluster_kernel for slabs beyond 16 quads per thread — batched UNet levels (8 x 64 x
+// 64 x 320 ran as five waves of register-resident clusters at 1.9 TB/s) and mid-sized VAE maps that fell back to the
+// two-launch path.  A thread walks its quads at a stride that keeps its channel quad fixed (blockDim = TY * q), so the
+// per-group bookkeeping is identical; the second pass reads the slab back from shared memory instead of registers.
+// =============================================================================================
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(640) gn_cluster_smem_kernel(GnApply a, int U, int q, int TY, int S) {
+  pdl_trigger();
+  DFU_TR_BEGIN(TR_GN_FUSED);
+  extern __shared__ __align__(16) float4 slab[];  // [pixel - p0][q]
+  __shared__ float s_w[20][kGnMaxU][2];
+  __shared__ __align__(16) double s_cta[kGnMaxU][2];
+  __shared__ float s_mean[kGnMaxU], s_rstd[kGnMaxU];
+  const int C = a.s.C0 + a.s.C1;
+  const int cpg = C / a.groups;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int unit = blockIdx.x / S;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int tx = tid % q, ty = tid / q;  // ty >= TY: spare threads of the last warp
+  const int cq = unit * q + tx;
+  const int c = cq * 4;
+  int gs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gs[k] = (c + k) / cpg - unit * U;
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  pdl_wait();
+  DFU_TR_MARK(6);
+  const int ppc = (a.s.HW + S - 1) / S;
+  const int p0 = rank * ppc;
+  const int p1 = min(p0 + ppc, a.s.HW);
+  if (ty < TY) {
+    const float* src = (c < a.s.C0) ? a.s.src0 + static_cast<size_t>(b) * a.s.HW * a.s.C0 + c
+                                    : a.s.src1 + static_cast<size_t>(b) * a.s.HW * a.s.C1 + (c - a.s.C0);
+    const int ld = (c < a.s.C0) ? a.s.C0 : a.s.C1;
+    for (int p = p0 + ty; p < p1; p += TY) cp_async16(&slab[(p - p0) * q + tx], src + static_cast<size_t>(p) * ld);
+  }
+  cp_async_wait_all();
+  float sx[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+  if (ty < TY) {
+    for (int p = p0 + ty; p < p1; p += TY) {  // (own copies only: no barrier needed before reading them back)
+      const float4 v = slab[(p - p0) * q + tx];
+      sx[0] += v.x; sq[0] += v.x * v.x;
+      sx[1] += v.y; sq[1] += v.y * v.y;
+      sx[2] += v.z; sq[2] += v.z * v.z;
+      sx[3] += v.w; sq[3] += v.w * v.w;
+    }
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int u = 0; u < kGnMaxU; ++u) {
+    if (u < U) {
+      float gsum = 0.f, gsq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (gs[k] == u) {
+          gsum += sx[k];
+          gsq += sq[k];
+        }
+      gsum = warp_sum(gsum);
+      gsq = warp_sum(gsq);
+      if (lane == 0) {
+        s_w[warp][u][0] = gsum;
+        s_w[warp][u][1] = gsq;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < U) {
+    double sd = 0.0, qd = 0.0;
+    for (int w = 0; w < nwarps; ++w) {
+      sd += s_w[w][tid][0];
+      qd += s_w[w][tid][1];
+    }
+    s_cta[tid][0] = sd;
+    s_cta[tid][1] = qd;
+  }
+  cluster_sync_all();
+  if (tid < U) {
+    double sd = 0.0, qd = 0.0;
+    const uint32_t loc = smem_u32(&s_cta[tid][0]);
+    double ps[8], pq[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t ra = dsmem_addr(loc, static_cast<uint32_t>(r < S ? r : 0));
+      ps[r] = ld_dsmem_f64(ra);
+      pq[r] = ld_dsmem_f64(ra + 8);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < S) {
+        sd += ps[r];
+        qd += pq[r];
+      }
+    }
+    const double mean = sd / a.count;
+    double var = qd / a.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + a.eps));
+  }
+  cluster_arrive();
+  __syncthreads();
+  DFU_TR_MARK(7);
+  if (ty < TY) {
+    const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+    const float be[4] = {be4.x, be4.y, be4.z, be4.w};
+    float mu[4], sc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mu[k] = s_mean[gs[k]];
+      sc[k] = s_rstd[gs[k]] * ga[k];
+    }
+    for (int p = p0 + ty; p < p1; p += TY) {
+      const float4 x = slab[(p - p0) * q + tx];
+      float4 y;
+      y.x = (x.x - mu[0]) * sc[0] + be[0];
+      y.y = (x.y - mu[1]) * sc[1] + be[1];
+      y.z = (x.z - mu[2]) * sc[2] + be[2];
+      y.w = (x.w - mu[3]) * sc[3] + be[3];
+      if (a.silu) {
+        y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+      }
+      const size_t off = (static_cast<size_t>(b) * a.s.HW + p) * C + c;
+      if (a.out16) store_split4(a.out16 + off, a.plane_stride, a.planes, y);
+      if (a.out32) *reinterpret_cast<float4*>(a.out32 + off) = y;
+      if (a.raw16) store_split4(a.raw16 + off, a.plane_stride, a.planes, x);
+    }
+  }
+  DFU_TR_END();
+  cluster_wait();
+}
+
+// =============================================================================================
 // LayerNorm over the channel dim of [M, C] tokens -> fp16 operand planes.  One warp per token, two-pass in registers.
 // =============================================================================================
 constexpr int kLnMaxQuads = 10;  // C <= 1280
@@ -609,6 +749,34 @@ static int gn_cluster_capacity(int S, int T, int variant) {
   return c;
 }
 
+// resident clusters of gn_cluster_smem_kernel for (S, T threads, dynamic smem); cached in a small table
+static int gn_smem_capacity(int S, int T, size_t smem) {
+  struct Key { int S, T; size_t smem; int cap; };
+  static Key cache[64];
+  static int n = 0;
+  for (int i = 0; i < n; ++i)
+    if (cache[i].S == S && cache[i].T == T && cache[i].smem == smem) return cache[i].cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S * 64, 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(S);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int c = 0;
+  if (cudaOccupancyMaxActiveClusters(&c, gn_cluster_smem_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    c = -1;
+  }
+  if (c <= 0) c = -1;
+  if (n < 64) cache[n++] = Key{S, T, smem, c};
+  return c;
+}
+
 extern "C" {
 
 size_t dfu_groupnorm_workspace(int B, int HW, int C, int groups) {
@@ -675,6 +843,49 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
         if (TYc >= 1 && (ppcS + TYc - 1) / TYc <= 16) {
           bestS = fs; bestTY = TYc; bestItems = (ppcS + TYc - 1) / TYc;
         }
+      }
+    }
+    // ---- shared-memory-staged variant: when the register-resident clusters would run as several waves (batched levels)
+    // or do not fit at all (maps that used to fall back to two launches) ----
+    static const bool smem_ok = !(getenv("DFU_GN_SMEM") && getenv("DFU_GN_SMEM")[0] == '0');
+    const long long nclusters = static_cast<long long>(nunits) * B;
+    double reg_us = 1e30;  // rough cost of the register path: ~7 us per wave of clusters (measured)
+    if (bestS > 0) reg_us = best / (bestItems + 6) * 7.0;
+    if (smem_ok && (bestS == 0 || reg_us >= 14.0)) {
+      if (first_use_on_device(ONCE_GN_SMEM_ATTR))
+        DFU_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      int sS = 0, sTY = 0;
+      size_t sBytes = 0;
+      double sBest = 1e30;
+      for (int S = 8; S >= 1; S >>= 1) {
+        const int ppcS = (HW + S - 1) / S;
+        if (ppcS * (S - 1) >= HW && S > 1) continue;
+        const size_t bytes = static_cast<size_t>(ppcS) * q * 16;
+        if (bytes > 200 * 1024) continue;
+        int TYc = 512 / q;
+        if (TYc > ppcS) TYc = ppcS;
+        if (TYc < 1) continue;
+        const int T = ((q * TYc + 31) / 32) * 32;
+        if (T > 640) continue;
+        const int cap = gn_smem_capacity(S, T, bytes);
+        if (cap <= 0) continue;
+        const double waves = static_cast<double>((nclusters + cap - 1) / cap);
+        const double us = waves * (3.0 + static_cast<double>(bytes) / (30.0 * 1024));  // load + two passes over the slab
+        if (us < sBest) {
+          sBest = us; sS = S; sTY = TYc; sBytes = bytes;
+        }
+      }
+      if (sS > 0 && sBest < reg_us) {
+        GnApply f;
+        f.s = s; f.groups = groups; f.stats = nullptr; f.partial = nullptr; f.nchunks = 0; f.pix_per_cta = 0;
+        f.count = static_cast<double>(cpg) * HW;
+        f.gamma = gamma; f.beta = beta; f.eps = eps; f.silu = silu;
+        f.out16 = static_cast<__half*>(out16); f.planes = planes; f.plane_stride = plane_stride;
+        f.out32 = out32; f.raw16 = static_cast<__half*>(raw16);
+        const int T = ((q * sTY + 31) / 32) * 32;
+        DFU_CHECK_CUDA(launch_kc(gn_cluster_smem_kernel, dim3(sS * nunits, B), dim3(T), sBytes, stream, sS, f, U, q, sTY, sS));
+        DFU_CHECK_CUDA(cudaGetLastError());
+        return DFU_OK;
       }
     }
     if (bestS > 0) {

@@ -16,7 +16,7 @@ import re
 import sys
 
 path = sys.argv[1]
-peak = float(sys.argv[2]) if len(sys.argv) > 2 else None
+peak = float(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].replace(".", "").isdigit() else None
 if peak is None:
     mp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     peak = json.load(open(mp))["hbm_gbs"] if os.path.exists(mp) else 6650.0
@@ -40,6 +40,13 @@ for d in per_launch.values():
 print(f"HBM peak used: {peak:.1f} GB/s (MEASURED_PEAKS.json)")
 print(f"{'kernel':34s} {'launches':>8s} {'time us':>9s} {'avg us':>7s} {'DRAM MB':>9s} {'L2 MB':>9s} {'DRAM GB/s':>10s} "
       f"{'of peak':>8s} {'L2 GB/s':>9s}")
+if "--json" in sys.argv:  # totals of the selected kernels, for bench.py's roofline.traffic
+    sel = sys.argv[sys.argv.index("--json") + 1]
+    n = sum(a["launches"] for k, a in agg.items() if sel in k)
+    tot = sum(a["dram_b"] for k, a in agg.items() if sel in k)
+    print(json.dumps({"kernels_matching": sel, "launches": int(n), "dram_bytes_total": tot,
+                      "dram_bytes_per_launch": tot / max(n, 1), "source": os.path.basename(path)}))
+    sys.exit(0)
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["time_s"]):
     t = a["time_s"]
     print(f"{name:34s} {a['launches']:8d} {t * 1e6:9.1f} {t * 1e6 / a['launches']:7.1f} {a['dram_b'] / 1e6:9.1f} "

@@ -9,7 +9,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--hw", type=int, default=64); ap.add_argument("--cin", type=int, default=320)
 ap.add_argument("--cout", type=int, default=320); ap.add_argument("--prec", type=int, default=1)
 ap.add_argument("--attn", action="store_true"); ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--tune", default="0,0,0", help="block_n,splits,stages[,kernel] (kernel 2 = persistent CTA pairs)")
 a = ap.parse_args()
+tune = tuple(int(v) for v in a.tune.split(","))
 dev = "cuda"
 if a.attn:
     B, heads, N = 1, 5, 4096
@@ -20,11 +23,11 @@ if a.attn:
 else:
     P = ops.planes_of(a.prec)
     H = W = a.hw
-    x16 = torch.randn(P, H, W, a.cin, device=dev).half()
+    x16 = torch.randn(P * a.batch, H, W, a.cin, device=dev).half()
     w16 = ops.pack_conv_weight(torch.randn(a.cout, a.cin, 3, 3, device=dev) * 0.02, P)
-    out = torch.empty(H * W, a.cout, device=dev)
+    out = torch.empty(a.batch * H * W, a.cout, device=dev)
     bias = torch.zeros(a.cout, device=dev)
     for _ in range(a.reps):
-        ops.conv(x16, w16, a.cout, a.prec, (1, H, W), ops.taps_3x3_s1(), out_f32=out, bias=bias)
+        ops.conv(x16, w16, a.cout, a.prec, (a.batch, H, W), ops.taps_3x3_s1(), tune=tune, out_f32=out, bias=bias)
 torch.cuda.synchronize()
 print("done")

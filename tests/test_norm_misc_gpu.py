@@ -31,6 +31,12 @@ def _rel(a, b):
     (1, 8, 8, 1280, 1280, True, 1e-5),     # 2560 channels
     (2, 16, 16, 1280, 0, False, 1e-6),     # Transformer2DModel.norm
     (1, 256, 256, 128, 0, True, 1e-6),     # VAE-sized
+    # slabs staged in shared memory (gn_cluster_smem_kernel): batched UNet levels and mid-sized VAE maps
+    (8, 64, 64, 320, 0, True, 1e-5),
+    (8, 32, 32, 640, 320, True, 1e-5),     # two-source concat through the cp.async path
+    (5, 64, 64, 640, 320, True, 1e-5),     # 960 channels at level 0 (odd batch)
+    (2, 128, 128, 512, 0, True, 1e-6),     # VAE decoder map: used to take the two-launch path
+    (3, 96, 96, 320, 0, False, 1e-6),      # 768-px latent, no SiLU
 ])
 def test_groupnorm(ops, planes, B, H, W, C0, C1, silu, eps):
     C = C0 + C1
@@ -55,7 +61,7 @@ def test_groupnorm(ops, planes, B, H, W, C0, C1, silu, eps):
 
 
 @pytest.mark.parametrize("planes", [1, 2])
-@pytest.mark.parametrize("M,C", [(4096, 320), (1024, 640), (77, 1280)])
+@pytest.mark.parametrize("M,C", [(4096, 320), (1024, 640), (77, 1280), (32768, 320), (9473, 640), (1154, 1024)])
 def test_layernorm(ops, planes, M, C):
     x = _rand((M, C), 5) * 2 + 0.3
     g = 1 + 0.1 * _rand((C,), 6)
