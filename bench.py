@@ -455,8 +455,11 @@ def run_gpu(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")  # ncu DRAM pass over one eager UNet step (B=1)
     if os.path.exists(tp) and B == 1:
-        with open(tp) as f:
-            traffic = json.load(f)["dram_bytes_per_launch"]
+        try:
+            with open(tp) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"]
+        except (ValueError, KeyError):
+            traffic = None
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv + linear)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": traffic, "traffic_note": "avg DRAM bytes per gemm launch over one UNet step (ncu, cold L2; "

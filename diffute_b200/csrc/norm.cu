@@ -875,7 +875,8 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
           sBest = us; sS = S; sTY = TYc; sBytes = bytes;
         }
       }
-      if (sS > 0 && sBest < reg_us) {
+      (void)reg_us;  // (measured: once the register path needs two waves the staged slab wins whenever it fits)
+      if (sS > 0) {
         GnApply f;
         f.s = s; f.groups = groups; f.stats = nullptr; f.partial = nullptr; f.nchunks = 0; f.pix_per_cta = 0;
         f.count = static_cast<double>(cpg) * HW;

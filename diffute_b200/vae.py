@@ -175,6 +175,16 @@ class AutoencoderKL:
                 pk.f32(sd[f"{a}.to_{x}.bias"].reshape(-1, 1), into=w[a + ".qkv.b"], row0=i * C)
         w["encoder.conv_out.wp"] = pk.small_out(sd["encoder.conv_out.weight"])
         w["decoder.conv_out.wp"] = pk.small_out(sd["decoder.conv_out.weight"])
+        # decoder output conv (128 -> 3 over the full-resolution map, 1.8 GFLOP at 512x512) on the tensor cores: output
+        # channels zero-padded to one 32-column tile; a 1x1 "selection" pass then adds the bias and writes NCHW
+        wo = sd["decoder.conv_out.weight"]
+        Pd = ops.planes_of(self.dec_prec)
+        w["decoder.conv_out.w16"] = torch.zeros((Pd * 32, wo.shape[1] * 9), dtype=torch.float16, device=self.device)
+        pk.weight16(wo, Pd, into=w["decoder.conv_out.w16"], row0=0, total_rows=32)
+        sel = torch.zeros((wo.shape[0], 1, 32), dtype=torch.float32)
+        for i in range(wo.shape[0]):
+            sel[i, 0, i] = 1.0
+        w["decoder.conv_out.sel"] = sel.to(self.device)
         for k in ("encoder.conv_in", "post_quant_conv", "decoder.conv_in"):
             w[k + ".wt"] = pk.small_in(sd[k + ".weight"])
         qw = sd["quant_conv.weight"]
@@ -329,11 +339,20 @@ class AutoencoderKL:
                          ops.taps_3x3_s1(), ws=self.ws, out_f32=out.view(-1, Ch), bias=w[k + ".bias"])
                 h = out
         Bh, Hh, Wh, Ch = h.shape
-        o32 = self._fp32([h], (Bh, Hh, Wh, Ch))
-        ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], 1e-6, True, self.prec,
-                      out32=o32, ws=self.ws)
         img = torch.empty((B, cfg["out_channels"], Hh, Wh), device=self.device, dtype=torch.float32)
-        ops.conv_small_out(o32, w["decoder.conv_out.wp"], w["decoder.conv_out.bias"], img)
+        if Ch % 64 == 0 and cfg["out_channels"] <= 8:
+            o16 = self._op16("opA", (B, Hh, Wh, Ch))
+            ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], 1e-6, True, self.prec,
+                          out16=o16, ws=self.ws)
+            t32 = self._fp32([h], (Bh, Hh, Wh, 32))
+            ops.conv(o16.view(P * B, Hh, Wh, Ch), w["decoder.conv_out.w16"], 32, self.prec, (B, Hh, Wh), ops.taps_3x3_s1(),
+                     ws=self.ws, out_f32=t32.view(-1, 32))
+            ops.conv_small_out(t32, w["decoder.conv_out.sel"], w["decoder.conv_out.bias"], img)
+        else:
+            o32 = self._fp32([h], (Bh, Hh, Wh, Ch))
+            ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], 1e-6, True, self.prec,
+                          out32=o32, ws=self.ws)
+            ops.conv_small_out(o32, w["decoder.conv_out.wp"], w["decoder.conv_out.bias"], img)
         return DecoderOutput(img) if return_dict else (img,)
 
     @torch.no_grad()

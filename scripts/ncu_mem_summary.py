@@ -37,9 +37,6 @@ for d in per_launch.values():
     a["time_s"] += d.get("gpu__time_duration.sum", 0.0)
     a["dram_b"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     a["l2_b"] += d.get("lts__t_bytes.sum", 0.0)
-print(f"HBM peak used: {peak:.1f} GB/s (MEASURED_PEAKS.json)")
-print(f"{'kernel':34s} {'launches':>8s} {'time us':>9s} {'avg us':>7s} {'DRAM MB':>9s} {'L2 MB':>9s} {'DRAM GB/s':>10s} "
-      f"{'of peak':>8s} {'L2 GB/s':>9s}")
 if "--json" in sys.argv:  # totals of the selected kernels, for bench.py's roofline.traffic
     sel = sys.argv[sys.argv.index("--json") + 1]
     n = sum(a["launches"] for k, a in agg.items() if sel in k)
@@ -47,6 +44,9 @@ if "--json" in sys.argv:  # totals of the selected kernels, for bench.py's roofl
     print(json.dumps({"kernels_matching": sel, "launches": int(n), "dram_bytes_total": tot,
                       "dram_bytes_per_launch": tot / max(n, 1), "source": os.path.basename(path)}))
     sys.exit(0)
+print(f"HBM peak used: {peak:.1f} GB/s (MEASURED_PEAKS.json)")
+print(f"{'kernel':34s} {'launches':>8s} {'time us':>9s} {'avg us':>7s} {'DRAM MB':>9s} {'L2 MB':>9s} {'DRAM GB/s':>10s} "
+      f"{'of peak':>8s} {'L2 GB/s':>9s}")
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["time_s"]):
     t = a["time_s"]
     print(f"{name:34s} {a['launches']:8d} {t * 1e6:9.1f} {t * 1e6 / a['launches']:7.1f} {a['dram_b'] / 1e6:9.1f} "
