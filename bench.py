@@ -212,6 +212,14 @@ def _event_ms(fn, n):
     return e0.elapsed_time(e1) / n
 
 
+def _median_call_ms(fn, warmup=2, n=3):
+    """Seconds-long calls (a whole batch of images): `warmup` untimed calls (the first replays of a freshly captured
+    graph and first-touch allocations are slower), then the median of `n` individually timed calls."""
+    for _ in range(warmup):
+        fn()
+    return statistics.median(_event_ms(fn, 1) for _ in range(n))
+
+
 def in_graph_class_ms(pipe, B, h, w, classes=("gemm", "attention", "groupnorm", "layernorm"), reps=20):
     """In-graph cost of each kernel class of one UNet step by ablation: the step is re-captured with that class's
     launches removed (same buffers, same order, PDL edges intact) and replayed; cost = full - ablated (CUDA events on the
@@ -243,8 +251,8 @@ def in_graph_class_ms(pipe, B, h, w, classes=("gemm", "attention", "groupnorm", 
 
 def extra_configs(pipe, dev, peaks):
     """BASELINE configs 3 (1-GPU leg: batch 8), 4 (VAE encode+decode, batch 32) and 5 (768x768, batch 4, CFG x2), each
-    with its own roofline sub-record.  Inputs are resident in HBM; CUDA events on the launch stream; one warm-up call,
-    two timed calls (each call is seconds of GPU work — far beyond L2, no flush needed)."""
+    with its own roofline sub-record.  Inputs are resident in HBM; CUDA events on the launch stream; warm-up calls, then
+    the median of three individually timed calls (each call is 0.3-2 s of GPU work — far beyond L2, no flush needed)."""
     import torch
     from diffute_b200 import synthetic
     out = {}
@@ -259,8 +267,7 @@ def extra_configs(pipe, dev, peaks):
     d = dev_inputs(B, PX)
     call = lambda: pipe(masked_image=d["masked_image"], mask_image=d["mask"], glyph_embeds=d["glyph_embeds"],
                         latents=d["latents"], posterior_noise=d["posterior_noise"], num_inference_steps=NSTEPS).images
-    call()
-    ms = _event_ms(call, 2)
+    ms = _median_call_ms(call)
     graph, _, _ = pipe._step_graph(B, PX // 8, PX // 8, True)
     graph.replay()
     step_ms = _event_ms(graph.replay, 10)
@@ -315,8 +322,7 @@ def extra_configs(pipe, dev, peaks):
     call = lambda: pipe(masked_image=d["masked_image"], mask_image=d["mask"], glyph_embeds=d["glyph_embeds"],
                         negative_glyph_embeds=neg, guidance_scale=2.0, latents=d["latents"],
                         posterior_noise=d["posterior_noise"], num_inference_steps=NSTEPS).images
-    call()
-    ms = _event_ms(call, 2)
+    ms = _median_call_ms(call, warmup=1, n=3)
     graph, _, _ = pipe._step_graph(2 * B, px // 8, px // 8, False)
     graph.replay()
     step_ms = _event_ms(graph.replay, 5)

@@ -665,7 +665,8 @@ int plan_gemm(const DfuGemm* d, Plan* pl) {
           if (d->n % c == 0 && (d->epi != DFU_EPI_GEGLU || c % 32 == 0)) { pbn = c; break; }
       }
       DFU_REQUIRE(d->splits <= 1, "gemm: the pair kernel has no split-K (splits=%d)", d->splits);
-    } else if (d->kernel == 0 && d->block_n <= 0 && d->splits <= 0) {
+    } else if (d->kernel == 0 && d->block_n <= 0 && d->splits <= 0 &&
+               !(getenv("DFU_GEMM_AUTO_PAIR") && getenv("DFU_GEMM_AUTO_PAIR")[0] == '0')) {
       const int cands[] = {256, 192, 160, 128};
       for (int c : cands)
         if (d->n % c == 0 && (d->epi != DFU_EPI_GEGLU || c % 32 == 0)) { pbn = c; break; }

@@ -848,10 +848,13 @@ int dfu_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, i
     // ---- shared-memory-staged variant: when the register-resident clusters would run as several waves (batched levels)
     // or do not fit at all (maps that used to fall back to two launches) ----
     static const bool smem_ok = !(getenv("DFU_GN_SMEM") && getenv("DFU_GN_SMEM")[0] == '0');
+    static const bool smem_force = getenv("DFU_GN_SMEM") && getenv("DFU_GN_SMEM")[0] == '2';  // experiments
     const long long nclusters = static_cast<long long>(nunits) * B;
     double reg_us = 1e30;  // rough cost of the register path: ~7 us per wave of clusters (measured)
     if (bestS > 0) reg_us = best / (bestItems + 6) * 7.0;
-    if (smem_ok && (bestS == 0 || reg_us >= 14.0)) {
+    // (measured at batch 1 too: the staged variant is equal or faster — 64x64x320 7.0 -> 6.2 us, 16x16x1280 3.7 -> 2.9 us —
+    // except for the 15-quad units of the 960 / 1920-channel concats)
+    if (smem_ok && (bestS == 0 || reg_us >= 14.0 || smem_force || q <= 10)) {
       if (first_use_on_device(ONCE_GN_SMEM_ATTR))
         DFU_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       int sS = 0, sTY = 0;
