@@ -106,6 +106,8 @@ class UNet2DConditionModel:
         self.arena = Arena(self.device)
         self._graphs = {}
         self._ctx_key = None
+        self._prefetch_plans = {}
+        self.weight_prefetch = os.environ.get("DFU_WEIGHT_PREFETCH", "1") != "0"
         self._weights_generation = 0
         self._sd = {k: state_dict[k].detach().to(torch.float32) for k in shapes}
         self._pack(self._sd)
@@ -247,6 +249,7 @@ class UNet2DConditionModel:
         self._sd = {k: state_dict[k].detach().to(torch.float32) for k in shapes}
         self._pack(self._sd)
         self._graphs.clear()          # captured steps hold the old packed-weight addresses
+        self._prefetch_plans.clear()
         self._weights_generation += 1
         self._ctx_key = None
         return self
@@ -439,6 +442,21 @@ class UNet2DConditionModel:
         """All launches of one denoising step against static buffers: `in.sample` [B,9,H,W] (or `srcs`, up to three
         NCHW tensors whose channel concat is the UNet input — the cat of app.ipynb:811 is then never materialised),
         `in.t` [B] and the prepared glyph context."""
+        A, w, cfg, lay = self.arena, self.w, self.config, self.layout
+        # weight prefetch plan of this launch sequence (recorded on the first walk, applied afterwards: every contraction
+        # asks L2 for the next one's weights while its own epilogue runs — the deep levels are weight-streaming bound)
+        plan = self._prefetch_plans.setdefault((B, H, W, self.n_ctx), ops.PrefetchPlan()) if self.weight_prefetch else None
+        if plan is not None:
+            plan.begin()
+        ops.PREFETCH = plan
+        try:
+            return self._forward_body(B, H, W, step_io, srcs, t, tproj)
+        finally:
+            ops.PREFETCH = None
+            if plan is not None:
+                plan.end()
+
+    def _forward_body(self, B, H, W, step_io, srcs, t, tproj):
         A, w, cfg, lay = self.arena, self.w, self.config, self.layout
         if srcs is None:
             srcs = [A.get("in.sample", (B, cfg["in_channels"], H, W))]

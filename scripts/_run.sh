@@ -1,6 +1,8 @@
-timeout 200 python scripts/exp_vae.py 8 2>&1 | grep -v Warn
-echo "--- DFU_GN_SMEM=0"; DFU_GN_SMEM=0 timeout 200 python scripts/exp_vae.py 8 2>&1 | grep -v Warn
-echo "--- DFU_GEMM_AUTO_PAIR=0"; DFU_GEMM_AUTO_PAIR=0 timeout 200 python scripts/exp_vae.py 8 2>&1 | grep -v Warn
-echo "--- B=1"; timeout 200 python scripts/exp_vae.py 1 2>&1 | grep -v Warn
-echo "--- GN B=1 reg vs smem"
-for shp in "64 64 320 1" "32 32 640 1" "16 16 1280 1" "64 64 960 1" "32 32 1920 1"; do DFU_TRACE=1 timeout 120 python scripts/bench_gn.py $shp 2>&1 | grep -E "GroupNorm|auto"; DFU_GN_SMEM=2 DFU_TRACE=1 timeout 120 python scripts/bench_gn.py $shp 2>&1 | grep -E "auto"; done
+timeout 900 python -m pytest tests/test_norm_misc_gpu.py tests/test_unet_gpu.py tests/test_pipeline_gpu.py -m gpu -q 2>&1 | tail -3
+python bench.py --steps 3 --warmup 3 > gpurun_out/r02i_bench.json 2> gpurun_out/r02i_bench.err; tail -c 300 gpurun_out/r02i_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02i_bench.json'))
+print(d['value'], d['e2e']['value'], d['roofline']['unet_step_ms'], d['roofline']['frac'], d['roofline']['in_graph_ms_per_unet_step'])
+for k,v in d['configs'].items(): print(k, {kk:(round(vv,2) if isinstance(vv,float) else vv) for kk,vv in v.items() if not isinstance(vv,(dict,str))}, v.get('in_graph_ms_per_unet_step'), (v.get('roofline_gemm') or {}).get('frac'))
+PY
