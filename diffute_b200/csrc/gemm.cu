@@ -220,47 +220,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // the prologue above overlapped the previous kernel; every role waits for it (griddepcontrol.wait) right before its
   // first access to data that kernel produced — the TMA producer only after it has requested the weight tiles
 
+  // k-block -> loads (shared by the producer warps)
+  const int kbg0 = p.g[0].kb_per_pass;
+  // k-block -> (group, tap, channel chunk) and the loads of that k-block (hi [+ lo] tile of each operand)
+  auto issue = [&](int kb, int stage, bool load_a, bool load_b) {
+    int r = kb, gi = 0;
+    if (r >= kbg0) {
+      r -= kbg0;
+      gi = 1;
+    }
+    const GroupDev& G = p.g[gi];
+    const int tap = r / G.nchunks;
+    const int chunk = r - tap * G.nchunks;
+    const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
+    const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
+    uint8_t* sA = smem + stage * stage_bytes;
+    uint8_t* sB = sA + nplane * kABytes;
+    if (load_b) {  // the k-block's first load also arms the barrier with the bytes of ALL its tiles
+      mbar_arrive_expect_tx(&full_bar[stage], nplane * (p.a_tx_bytes[gi] + p.b_tx_bytes));
+      for (uint32_t pl = 0; pl < nplane; ++pl)
+        tma_load_2d(sB + pl * b_bytes, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK,
+                    n_tile0 + b_off + static_cast<int>(pl) * G.b_plane);
+    }
+    if (load_a) {
+      for (uint32_t pl = 0; pl < nplane; ++pl) {
+        const int a_sel = static_cast<int>(pl) * G.a_plane;
+        if (G.a_mode == 0) {
+          tma_load_2d(sA + pl * kABytes, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, a_row0 + a_sel);
+        } else {
+          tma_load_4d(sA + pl * kABytes, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
+                      img0 + G.dn[tap] + a_sel);
+        }
+      }
+    }
+  };
+  const bool pre = p.g[0].b_static && (p.ngroups == 1 || p.g[1].b_static);
+  const int npre = pre ? min(p.stages, kb1 - kb0) : 0;
+  // two producer lanes (p.two_prod): warp 0 streams the weight tiles (and arms the barriers), the first epilogue warp —
+  // idle during the main loop — streams the activation tiles: a single issuing lane sustains only ~55 GB/s of TMA
+  // traffic (~1 box row per 3.5 cycles), two lanes run in parallel
+  const bool two_prod = p.two_prod != 0;
+
   if (warp == 0) {
     // ===== TMA producer: the whole warp walks the k-blocks, one elected lane issues =============
     {
-      const int kbg0 = p.g[0].kb_per_pass;
-      // k-block -> (group, tap, channel chunk) and the loads of that k-block (hi [+ lo] tile of each operand)
-      auto issue = [&](int kb, int stage, bool load_a, bool load_b) {
-        int r = kb, gi = 0;
-        if (r >= kbg0) {
-          r -= kbg0;
-          gi = 1;
-        }
-        const GroupDev& G = p.g[gi];
-        const int tap = r / G.nchunks;
-        const int chunk = r - tap * G.nchunks;
-        const CUtensorMap* mA = gi ? &tmA1 : &tmA0;
-        const CUtensorMap* mB = gi ? &tmB1 : &tmB0;
-        uint8_t* sA = smem + stage * stage_bytes;
-        uint8_t* sB = sA + nplane * kABytes;
-        if (load_b) {  // the k-block's first load also arms the barrier with the bytes of ALL its tiles
-          mbar_arrive_expect_tx(&full_bar[stage], nplane * (p.a_tx_bytes[gi] + p.b_tx_bytes));
-          for (uint32_t pl = 0; pl < nplane; ++pl)
-            tma_load_2d(sB + pl * b_bytes, mB, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK,
-                        n_tile0 + b_off + static_cast<int>(pl) * G.b_plane);
-        }
-        if (load_a) {
-          for (uint32_t pl = 0; pl < nplane; ++pl) {
-            const int a_sel = static_cast<int>(pl) * G.a_plane;
-            if (G.a_mode == 0) {
-              tma_load_2d(sA + pl * kABytes, mA, &full_bar[stage], (tap * G.nchunks + chunk) * kBlockK, a_row0 + a_sel);
-            } else {
-              tma_load_4d(sA + pl * kABytes, mA, &full_bar[stage], chunk * kBlockK, x0 + G.dx[tap], y0 + G.dy[tap],
-                          img0 + G.dn[tap] + a_sel);
-            }
-          }
-        }
-      };
       // Weights do not depend on the previous kernel: the B tiles of the first ring-full of k-blocks are requested
       // BEFORE griddepcontrol.wait, so their HBM latency (and, for the weight-streaming deep levels, a good part of
       // the streaming itself) overlaps the producer kernel's tail.
-      const bool pre = p.g[0].b_static && (p.ngroups == 1 || p.g[1].b_static);
-      const int npre = pre ? min(p.stages, kb1 - kb0) : 0;
       if (elect_one())
         for (int i = 0; i < npre; ++i) issue(kb0 + i, i, false, true);
       __syncwarp();
@@ -270,10 +276,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (kb - kb0 < npre) {
-          if (elect_one()) issue(kb, stage, true, false);
+          if (!two_prod && elect_one()) issue(kb, stage, true, false);
         } else {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (elect_one()) issue(kb, stage, true, true);
+          if (elect_one()) issue(kb, stage, !two_prod, true);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -289,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], phase);  // (probing back to back instead of backing off: measured, no difference)
         tc_fence_after();
         if (lane == 0 && kb == kb0) DFU_TR_SHARED_MARK(7);
         const uint32_t sA = smem_u32(smem + stage * stage_bytes);
@@ -381,6 +387,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     };
 #pragma unroll
     for (int it = 0; it < 8; ++it) res[it] = fetch_res1(cg * 32, it);
+    if (two_prod && warp == 2) {  // activation-tile producer (see above); done long before the accumulator is
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (kb - kb0 >= npre) mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) issue(kb, stage, true, false);
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
     mbar_wait_sleep(&tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) DFU_TR_SHARED_MARK(8);
@@ -904,6 +923,9 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   p.tiles_y = pl.tiles_y;
   p.b_tx_bytes = static_cast<uint32_t>(pl.block_n) * kBlockK * 2;
   fill_batch_dev(d, p.bt);
+  // (measured: 84 -> 74 us for a one-CTA-per-SM conv with a 6-deep ring, -1 % on the contraction class of the step)
+  static const int two_prod = getenv("DFU_GEMM_2PROD") ? atoi(getenv("DFU_GEMM_2PROD")) : 1;
+  p.two_prod = two_prod;
   p.pf_ptr = static_cast<const uint8_t*>(d->prefetch);
   p.pf_bytes = d->prefetch ? d->prefetch_bytes : 0;
   uint32_t cols = 32;

@@ -69,6 +69,7 @@ struct GemmKernelParams {
   uint32_t tmem_cols;
   float* ws;
   BatchDev bt;
+  int two_prod;           // 1: weight tiles and activation tiles are issued by two different warps
   const uint8_t* pf_ptr;  // L2 prefetch request for the next layer's weights (or null)
   long long pf_bytes;
   int cluster;         // > 1: the `splits` K-slices of a tile form a thread-block cluster and reduce through DSMEM
