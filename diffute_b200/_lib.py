@@ -39,7 +39,6 @@ class Gemm(C.Structure):
         ("out_f32", C.c_void_p), ("ldo", C.c_int32),
         ("out_f16", C.c_void_p), ("ldh", C.c_int32), ("out_planes", C.c_int32), ("out_plane_stride", C.c_int64),
         ("block_n", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32), ("kernel", C.c_int32),
-        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("sync_words", C.c_void_p),
     ]
 

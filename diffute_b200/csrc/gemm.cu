@@ -403,16 +403,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_wait_sleep(&tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) DFU_TR_SHARED_MARK(8);
-    if (p.pf_ptr != nullptr) {
-      // this CTA's main loop is over: ask L2 for its slice of the NEXT layer's weights (128-byte lines), so that their HBM
-      // traffic runs under this kernel's epilogue, the split-K reduction and the normalisation kernel in between
-      const long long lines = (p.pf_bytes + 127) >> 7;
-      const long long per = (lines + gridDim.x - 1) / gridDim.x;
-      const long long l0 = static_cast<long long>(blockIdx.x) * per;
-      const long long l1 = l0 + per < lines ? l0 + per : lines;
-      for (long long l = l0 + (threadIdx.x - 64); l < l1; l += kEpiThreads)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_ptr + (l << 7)));
-    }
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // TMEM gives each thread one output row; a per-warp smem transpose turns that into row-contiguous 16-byte
     // quads per lane so global traffic is coalesced (4 full 128-byte lines per warp instruction).
@@ -926,8 +916,6 @@ static int run_gemm(const DfuGemm* d, cudaStream_t stream) {
   // (measured: 84 -> 74 us for a one-CTA-per-SM conv with a 6-deep ring, -1 % on the contraction class of the step)
   static const int two_prod = getenv("DFU_GEMM_2PROD") ? atoi(getenv("DFU_GEMM_2PROD")) : 1;
   p.two_prod = two_prod;
-  p.pf_ptr = static_cast<const uint8_t*>(d->prefetch);
-  p.pf_bytes = d->prefetch ? d->prefetch_bytes : 0;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(pl.block_n)) cols <<= 1;
   p.tmem_cols = cols;

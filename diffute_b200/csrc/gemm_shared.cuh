@@ -70,8 +70,6 @@ struct GemmKernelParams {
   float* ws;
   BatchDev bt;
   int two_prod;           // 1: weight tiles and activation tiles are issued by two different warps
-  const uint8_t* pf_ptr;  // L2 prefetch request for the next layer's weights (or null)
-  long long pf_bytes;
   int cluster;         // > 1: the `splits` K-slices of a tile form a thread-block cluster and reduce through DSMEM
   unsigned int* sync;  // grid-barrier words (zero between launches); non-null => fused split-K second stage
   EpiParams e;

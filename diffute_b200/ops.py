@@ -295,42 +295,7 @@ def gemm_key(d: Gemm) -> str:
     return f"{d.conv}:{d.m}:{d.n}:{kb}:{d.epi}" + (f":b{d.batch}" if d.batch > 1 else "")
 
 
-# Weight prefetch plan: a static launch sequence (one UNet step) is walked once in "record" mode — every contraction
-# appends (weight pointer, bytes) — and afterwards in "apply" mode, where launch i carries the weights of launch i + 1 as
-# an L2 prefetch request (DfuGemm.prefetch).  Set by UNet2DConditionModel._forward_impl; None everywhere else.
-PREFETCH = None
-PREFETCH_MIN_BYTES = 1 << 20
-
-
-class PrefetchPlan:
-    def __init__(self):
-        self.seq, self.idx, self.recording = [], 0, True
-
-    def begin(self):
-        self.idx = 0
-
-    def visit(self, d: Gemm):
-        g0 = d.g[0]
-        w = (g0.b, g0.b_rows * g0.b_ld * 2) if g0.b_static else (0, 0)
-        if self.recording:
-            self.seq.append(w)
-            return
-        i = self.idx
-        self.idx += 1
-        if i >= len(self.seq) or self.seq[i][0] != w[0]:
-            self.seq, self.recording = [], True   # the sequence changed (other shapes): record again next time
-            return
-        if i + 1 < len(self.seq) and self.seq[i + 1][1] >= PREFETCH_MIN_BYTES:
-            d.prefetch, d.prefetch_bytes = self.seq[i + 1]
-
-    def end(self):
-        if self.recording and self.seq:
-            self.recording = False
-
-
 def launch_gemm(d: Gemm, ws: Optional[Workspace] = None):
-    if PREFETCH is not None:
-        PREFETCH.visit(d)
     L = lib()
     ws = ws or default_workspace()
     d.sync_words = ws.sync.data_ptr()

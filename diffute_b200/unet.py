@@ -106,11 +106,6 @@ class UNet2DConditionModel:
         self.arena = Arena(self.device)
         self._graphs = {}
         self._ctx_key = None
-        self._prefetch_plans = {}
-        # next-layer weight prefetch into L2 (ops.PrefetchPlan): built, measured on B200 in the captured step and left OFF —
-        # 3.44 ms with vs 3.36 ms without (the request burst at the end of every contraction competes with the split-K
-        # partials and the normalisation kernel for L2 / HBM); DFU_WEIGHT_PREFETCH=1 re-enables it for experiments
-        self.weight_prefetch = os.environ.get("DFU_WEIGHT_PREFETCH", "0") == "1"
         self._weights_generation = 0
         self._sd = {k: state_dict[k].detach().to(torch.float32) for k in shapes}
         self._pack(self._sd)
@@ -252,7 +247,6 @@ class UNet2DConditionModel:
         self._sd = {k: state_dict[k].detach().to(torch.float32) for k in shapes}
         self._pack(self._sd)
         self._graphs.clear()          # captured steps hold the old packed-weight addresses
-        self._prefetch_plans.clear()
         self._weights_generation += 1
         self._ctx_key = None
         return self
@@ -445,21 +439,6 @@ class UNet2DConditionModel:
         """All launches of one denoising step against static buffers: `in.sample` [B,9,H,W] (or `srcs`, up to three
         NCHW tensors whose channel concat is the UNet input — the cat of app.ipynb:811 is then never materialised),
         `in.t` [B] and the prepared glyph context."""
-        A, w, cfg, lay = self.arena, self.w, self.config, self.layout
-        # weight prefetch plan of this launch sequence (recorded on the first walk, applied afterwards: every contraction
-        # asks L2 for the next one's weights while its own epilogue runs — the deep levels are weight-streaming bound)
-        plan = self._prefetch_plans.setdefault((B, H, W, self.n_ctx), ops.PrefetchPlan()) if self.weight_prefetch else None
-        if plan is not None:
-            plan.begin()
-        ops.PREFETCH = plan
-        try:
-            return self._forward_body(B, H, W, step_io, srcs, t, tproj)
-        finally:
-            ops.PREFETCH = None
-            if plan is not None:
-                plan.end()
-
-    def _forward_body(self, B, H, W, step_io, srcs, t, tproj):
         A, w, cfg, lay = self.arena, self.w, self.config, self.layout
         if srcs is None:
             srcs = [A.get("in.sample", (B, cfg["in_channels"], H, W))]

@@ -108,11 +108,6 @@ typedef struct DfuGemm {
   int32_t kernel;          /* 0: choose; 1: one 128 x block_n tile per CTA (split-K slices reduce inside a thread-block
                               cluster); 2: persistent CTA pairs — tcgen05 cta_group::2, 256 x block_n tiles, two TMEM
                               accumulators so a tile's epilogue overlaps the next tile's main loop (splits must be 1) */
-  const void* prefetch;    /* optional: a byte range (the NEXT contraction's weights) requested into L2 by this launch's
-                              epilogue warps once its own main loop is over — at batch 1 the deep UNet levels are bound by
-                              streaming 30-60 MB of weights per layer while HBM idles through the neighbouring
-                              normalisation / reduction kernels; the 126 MB L2 holds a layer ahead */
-  int64_t prefetch_bytes;
   void* workspace;         /* fp32 [splits, m, n] when splits > 1 */
   size_t workspace_bytes;
   void* sync_words;        /* reserved (accepted and ignored): backed a grid-barrier second stage that was measured
