@@ -276,6 +276,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem_Sown = tmem_S + 64 * wg + lane_off;
     const uint32_t tmem_Oown = tmem_O + 64 * wg + lane_off;
     int g = 0;
+#ifdef DFU_TRACE
+    long long tr_ws = 0, tr_wo = 0, tr_cmp = 0, tr_n = 0, tr_t = 0;  // thread 0: cycles waiting for S / for P V, computing
+#endif
     for (long long u = u_begin; u < u_end;) {
       int item, jb0, nblk, b, head, q0;
       seg_of(u, item, jb0, nblk);
@@ -285,16 +288,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int c = 0;
       for (int gg = g + ((g & 1) != wg ? 1 : 0); gg < g + nblk; gg += 2, ++nown) {
         c = gg >> 1;                  // this warpgroup's block counter over the whole range
+#ifdef DFU_TRACE
+        tr_t = clock64();
+#endif
         mbar_wait(&s_full[wg], c & 1);
         tc_fence_after();
+#ifdef DFU_TRACE
+        { const long long t = clock64(); tr_ws += t - tr_t; tr_t = t; }
+#endif
         const int kv_valid = p.Nk - (jb0 + (gg - g)) * kBKV;  // columns >= kv_valid are padding
         const bool full = kv_valid >= kBKV;                   // warp-uniform: interior blocks skip the tail predicates
         // P_wg V of the previous own block must be finished before the P tile is overwritten (and before O_wg is
-        // touched); it was issued a whole block ago, so this does not stall
+        // touched).  It was issued right after this block's Q K^T and completes ~450-550 cycles after S arrives
+        // (scripts/exp_attn_phases.py).  Computing the first 32 probabilities into registers before this wait was
+        // measured: the wait disappears but the block's compute phase grows by more (1830 -> 2480 cycles, spills at 96
+        // registers), so it stays here
         if (nown > 0) {
           mbar_wait(&o_full[wg], (c - 1) & 1);
           tc_fence_after();
         }
+#ifdef DFU_TRACE
+        { const long long t = clock64(); tr_wo += t - tr_t; tr_t = t; }
+#endif
         if (nown == 0) {
           // first own block of a segment: the reference is its exact max (one extra read of S per segment)
           float mx = -INFINITY;
@@ -396,6 +411,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_proxy_async_smem();   // make P visible to the tensor-core (async) proxy
         mbar_arrive(&p_full[wg]);
         l += rowsum;
+#ifdef DFU_TRACE
+        tr_cmp += clock64() - tr_t;
+        ++tr_n;
+#endif
       }
       // ---- end of the segment: merge the two partial results of every row ----
       if (nown > 0) {
@@ -462,6 +481,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       g += nblk;
       u += nblk;
     }
+#ifdef DFU_TRACE
+    if (_tr) {  // (thread 0 = warpgroup 0, row 0) sums over its own blocks
+      _tr[12] = tr_ws;
+      _tr[13] = tr_wo;
+      _tr[14] = tr_cmp;
+      _tr[15] = tr_n;
+    }
+#endif
   }
 
   tc_fence_before();
