@@ -442,6 +442,38 @@ def patchify_f16(x: torch.Tensor, patch: int, out16: torch.Tensor):
 CAST_PLAIN, CAST_UP2X, CAST_S2D = 0, 1, 2
 
 
+def glue_preprocess(image_u8: torch.Tensor, window, bbox, out_size: int = 512, lat_factor: int = 8):
+    """image_u8 uint8 [h, w, 3] on the device; window = (x_s, y_s, cw, ch) clipped to the image; bbox = (x0, y0, x1, y1)
+    inclusive.  -> (image [3,S,S], masked [3,S,S], mask [1,S,S], mask_lat [1,S/f,S/f]) fp32 (dfu_glue_preprocess)."""
+    h, w, c = image_u8.shape
+    assert c == 3 and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()
+    S, dev = out_size, image_u8.device
+    img = torch.empty((3, S, S), dtype=torch.float32, device=dev)
+    msk_img = torch.empty((3, S, S), dtype=torch.float32, device=dev)
+    mask = torch.empty((1, S, S), dtype=torch.float32, device=dev)
+    mask_lat = torch.empty((1, S // lat_factor, S // lat_factor), dtype=torch.float32, device=dev)
+    x_s, y_s, cw, ch = window
+    with _Prof("glue_preprocess", 1):
+        check(lib().dfu_glue_preprocess(image_u8.data_ptr(), h, w, x_s, y_s, cw, ch, *(int(v) for v in bbox), S, lat_factor,
+                                        img.data_ptr(), msk_img.data_ptr(), mask.data_ptr(), mask_lat.data_ptr(),
+                                        _stream()), "dfu_glue_preprocess")
+    return img, msk_img, mask, mask_lat
+
+
+def glue_composite(decoded: torch.Tensor, image_u8: torch.Tensor, origin, size, bbox, wrap: bool = False) -> torch.Tensor:
+    """decoded fp32 [3, S, S] in [-1, 1]; image_u8 uint8 [h, w, 3]; origin = (x_s, y_s), size = (r_w, r_h) of the pasted
+    region; bbox = numpy-slice corners (end exclusive).  -> uint8 [h, w, 3] (dfu_glue_composite)."""
+    h, w, _ = image_u8.shape
+    S = decoded.shape[-1]
+    assert decoded.dtype == torch.float32 and decoded.is_contiguous() and decoded.shape == (3, S, S)
+    out = torch.empty_like(image_u8)
+    with _Prof("glue_composite", 1):
+        check(lib().dfu_glue_composite(decoded.data_ptr(), S, image_u8.data_ptr(), h, w, origin[0], origin[1], size[0],
+                                       size[1], *(int(v) for v in bbox), int(wrap), out.data_ptr(), _stream()),
+              "dfu_glue_composite")
+    return out
+
+
 def cast_f16(x: torch.Tensor, mode: int, out16: torch.Tensor):
     """x [B,H,W,C] fp32 NHWC -> out16 [planes, ...] (plain: B,H,W,C; up2x: B,2H,2W,C; s2d: 4*B,H/2,W/2,C)."""
     B, H, W, Cc = x.shape

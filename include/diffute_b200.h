@@ -194,6 +194,23 @@ int dfu_softmax_rows(const float* s, int rows, int n, int lds, float scale, void
 int dfu_transpose_f16(const void* in, int planes, int rows, int cols, int ld_in, int64_t in_plane, void* out,
                       int64_t out_plane, void* stream);
 
+/* ---- the reference's pre-/post-processing around the loop, on the GPU ---------------
+ * text_editing, /root/reference/app.ipynb:705-748: window [y_s, y_s+ch) x [x_s, x_s+cw) of the uint8 HWC photograph
+ * (already clipped to the image) -> alb.Resize(out_size, out_size) = cv2.resize INTER_LINEAR on uint8 (OpenCV's 11-bit
+ * fixed point, bit-exact) -> alb.Normalize(0.5, 0.5) -> ToTensorV2.  image_out / masked_out [3][S][S] fp32 in [-1, 1]
+ * (masked: pixels under the text box (bx0, by0)-(bx1, by1), both corners INCLUSIVE as PIL's rectangle, app.ipynb:370-383,
+ * are zeroed before the resize), mask_out [S][S] the resized 0/1 mask, mask_lat [S/f][S/f] its nearest-neighbour
+ * reduction to the latent grid (app.ipynb:787-790).  Any output may be NULL. */
+int dfu_glue_preprocess(const uint8_t* image, int h, int w, int x_s, int y_s, int cw, int ch, int bx0, int by0,
+                        int bx1, int by1, int out_size, int lat_factor, float* image_out, float* masked_out,
+                        float* mask_out, float* mask_lat, void* stream);
+/* app.ipynb:821-841: decoded [3][S][S] fp32 in [-1, 1] -> (x / 2 + 0.5) * 255 -> cv2.resize on float32 to (r_w, r_h)
+ * (double-precision fraction, fused multiply-add lerp, horizontal pass first: what the IPP build of the wheel
+ * computes) -> pasted at (x_s, y_s) -> of that only the numpy slice [by0:by1, bx0:bx1] (end EXCLUSIVE) replaces the
+ * photograph -> round half to even -> uint8 (wrap != 0: modulo 256 like numpy's astype; 0: clamped).  out [h][w][3]. */
+int dfu_glue_composite(const float* decoded, int S, const uint8_t* image, int h, int w, int x_s, int y_s, int r_w,
+                       int r_h, int bx0, int by0, int bx1, int by1, int wrap, uint8_t* out, void* stream);
+
 /* ---- fused attention core (head dim 64) --------------------------------------------------------
  * out[b, q, h*64:(h+1)*64] = softmax(Q_h K_h^T * scale) V_h for every sample b and head h: diffusers `Attention`
  * core of BasicTransformerBlock.attn1 (self, Nk = Nq = H*W) and attn2 (cross, Nk = 577 glyph tokens), SURVEY A.1,

@@ -1,0 +1,111 @@
+"""GPU parity of the reference's pre-/post-processing kernels (dfu_glue_preprocess / dfu_glue_composite, through the
+C-ABI) against oracle/glue.py, which tests/test_glue_oracle.py pins to cv2 / PIL: bit-exact for the uint8 path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from diffute_b200 import glue
+    from oracle import glue as G
+    return glue, G
+
+
+CASES = [  # (h, w, bbox, window or None)
+    (600, 800, (300, 250, 420, 290), None),          # 6 * 40 = 240 < 256: 256 window, 2x upscale
+    (300, 260, (10, 20, 200, 60), None),             # window = 256 at the origin
+    (1100, 1300, (100, 100, 900, 330), None),        # 6 * 230 >= 1000: window = short side, clipped
+    (512, 512, (400, 450, 500, 500), None),          # 384 window
+    (1400, 1500, (200, 300, 700, 400), (150, 100, 1024)),   # exactly 2x decimation: OpenCV's area fast path
+    (700, 900, (100, 100, 300, 150), (50, 60, 512)),        # identity resize
+    (640, 480, (380, 500, 470, 560), (300, 420, 384)),      # window clipped at both borders: 180 x 220 crop, non-square
+    (130, 97, (0, 0, 96, 129), (0, 0, 97)),                 # box = whole image (inclusive corners), tiny photograph
+    (520, 520, (3, 3, 4, 4), (0, 0, 2)),                    # 2 x 2 window: every destination pixel clamps
+]
+
+
+@pytest.mark.parametrize("h,w,bbox,window", CASES)
+def test_preprocess_bit_exact(mods, h, w, bbox, window):
+    glue, G = mods
+    rng = np.random.default_rng(h * 7 + w)
+    image = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    win = window if window is not None else G.crop_window(bbox, h, w, np.random.RandomState(0))
+    assert win == (window if window is not None else glue.crop_window(bbox, h, w, np.random.RandomState(0)))
+    pre = glue.preprocess(image, bbox, window=win)
+    torch.cuda.synchronize()
+    img_c, mim_c, msk_c = G.preprocess(image, bbox, win)
+    assert np.array_equal(pre.image[0].cpu().numpy(), img_c)
+    assert np.array_equal(pre.masked_image[0].cpu().numpy(), mim_c)
+    assert np.array_equal(pre.mask[0].cpu().numpy(), msk_c.astype(np.float32))
+    assert np.array_equal(pre.mask_latents[0, 0].cpu().numpy(), msk_c[0, ::8, ::8].astype(np.float32))
+    assert set(np.unique(msk_c).tolist()) <= {0, 1}
+
+
+@pytest.mark.parametrize("h,w,bbox,window", CASES)
+@pytest.mark.parametrize("wrap", [False, True])
+def test_composite_matches_oracle(mods, h, w, bbox, window, wrap):
+    glue, G = mods
+    rng = np.random.default_rng(h * 11 + w)
+    image = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    win = window if window is not None else G.crop_window(bbox, h, w, np.random.RandomState(0))
+    decoded = (rng.random((3, 512, 512), dtype=np.float32) * 2.4 - 1.2).astype(np.float32)   # leaves [-1, 1]: clamp / wrap
+    pre = glue.preprocess(image, bbox, window=win)
+    got = glue.composite(torch.from_numpy(decoded).cuda()[None], pre, wrap=wrap).cpu().numpy()
+    ref = G.composite(decoded, image, bbox, win, wrap=wrap)
+    assert got.shape == ref.shape == (h, w, 3) and got.dtype == np.uint8
+    x1, y1, x2, y2 = bbox
+    outside = np.ones((h, w), bool)
+    outside[y1:y2, x1:x2] = False
+    assert np.array_equal(got[outside], image[outside])          # nothing but the text box changes
+    # the float resize is a true fma on the device and an fma emulated in float64 in the oracle: identical except, at
+    # most, a rounding tie once in 2^29 pixels
+    assert (got != ref).mean() <= 1e-6, (got != ref).mean()
+
+
+def test_rejects_bad_geometry(mods):
+    glue, G = mods
+    from diffute_b200._lib import DfuError
+    image = np.zeros((64, 64, 3), np.uint8)
+    with pytest.raises(ValueError):
+        glue.preprocess(image, (1, 1, 5, 5), window=(70, 0, 32))
+    with pytest.raises(ValueError):
+        glue.preprocess(image.astype(np.float32), (1, 1, 5, 5))
+    from diffute_b200 import ops
+    with pytest.raises(DfuError):
+        ops.glue_preprocess(torch.zeros((64, 64, 3), dtype=torch.uint8, device="cuda"), (40, 0, 32, 32), (1, 1, 5, 5))
+
+
+def test_text_editing_end_to_end(mods):
+    """The reference's text_editing (app.ipynb:653-856) on the engine: photograph -> window -> 512 x 512 tensors ->
+    4 DDIM steps -> decode -> composite, against the same chain on the CPU oracle."""
+    glue, G = mods
+    from diffute_b200 import arch, synthetic
+    from diffute_b200.pipeline import DiffUTEPipeline
+    from oracle import DDIMOracle, UNetOracle, VAEOracle, sample_loop
+    usd = synthetic.make_state_dict(arch.unet_param_shapes())
+    vsd = synthetic.make_state_dict(arch.vae_param_shapes())
+    pipe = DiffUTEPipeline.from_synthetic("fp16x2", "fp16x2", state_dicts=(usd, vsd))
+    rng = np.random.default_rng(3)
+    h, w, bbox = 420, 560, (200, 180, 330, 215)
+    image = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    inp = synthetic.make_inputs(1, 512, 512)
+    edited, mask255 = glue.text_editing(pipe, None, image, 4, *bbox, glyph_embeds=inp["glyph_embeds"],
+                                        latents=inp["latents"], posterior_noise=inp["posterior_noise"])
+    assert edited.shape == (h, w, 3) and edited.dtype == np.uint8 and mask255.max() == 255
+    assert np.array_equal(mask255 // 255, G.generate_mask(h, w, bbox))
+    uo, vo = UNetOracle(), VAEOracle()
+    uo.load_state_dict(usd)
+    vo.load_state_dict(vsd)
+    win = G.crop_window(bbox, h, w)
+    _, mim_c, msk_c = G.preprocess(image, bbox, win)
+    dec = sample_loop(uo, vo, DDIMOracle(), torch.from_numpy(mim_c)[None], torch.from_numpy(msk_c.astype(np.float32))[None],
+                      inp["glyph_embeds"], inp["latents"], 4, posterior_noise=inp["posterior_noise"])
+    ref = G.composite(dec[0].numpy(), image, bbox, win)
+    diff = np.abs(edited.astype(int) - ref.astype(int))
+    print(f"text_editing vs oracle chain: pixels differing {(diff > 0).mean():.2e}, max |diff| {diff.max()}")
+    assert diff.max() <= 1 and (diff > 0).mean() < 2e-3   # decoded RGB agrees to ~1e-5: only rounding ties move
