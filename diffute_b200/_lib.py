@@ -104,7 +104,8 @@ SIGNATURES = {
     "dfu_gemv": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "dfu_conv_small_in": (_i, [_vp, _i, _i64, _vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp,
                                _vp]),
-    "dfu_conv_small_out": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "dfu_conv_small_out": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dfu_philox_normal": (_i, [C.c_uint64, C.c_uint32, _i64, _vp, _vp, _vp]),
     "dfu_glue_preprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "dfu_glue_composite": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dfu_axpbypcz": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64, _vp]),

@@ -179,6 +179,58 @@ conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Counter-based Gaussian noise for the ancestral DDPM step (app.ipynb:816 draws it with torch.randn on the device):
+// Philox4x32-10 (Salmon et al. 2011; key = 64-bit seed, counter = (element index lo, hi, step, 0)) -> two 24-bit
+// uniforms in (0, 1) -> Box-Muller cosine branch.  A pure function of (seed, step, element): no state, no extra launch,
+// the same stream whatever the tiling.  Restated in numpy and checked against the Random123 known-answer vectors.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__device__ __forceinline__ float philox_normal(uint32_t seed_lo, uint32_t seed_hi, uint32_t step, unsigned long long idx,
+                                               uint32_t* bits = nullptr) {
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), step, 0u, seed_lo, seed_hi, r);
+  if (bits) {
+    bits[0] = r[0];
+    bits[1] = r[1];
+  }
+  const float u1 = (static_cast<float>(r[0] >> 8) + 0.5f) * 5.9604644775390625e-8f;  // (k + 0.5) / 2^24 in (0, 1)
+  const float u2 = (static_cast<float>(r[1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t step, long long n,
+                                                            float* __restrict__ out, uint32_t* __restrict__ bits) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t b[2];
+    const float z = philox_normal(seed_lo, seed_hi, step, static_cast<unsigned long long>(i), b);
+    if (out) out[i] = z;
+    if (bits) {
+      bits[2 * i] = b[0];
+      bits[2 * i + 1] = b[1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Few-output-channel conv: NHWC fp32 in (Cin multiple of 128... any multiple of 4) -> NCHW fp32 out (Cout <= 8),
 // optional fused second 1x1 conv on the result (VAE quant_conv), optional fused scheduler update
 // (x' = cx * x + ce * eps) so the UNet's conv_out writes the next latents directly.
@@ -196,7 +248,8 @@ struct SmallOut {
   // fused scheduler step (optional): sample/prev are NCHW [B,Cout,H,W]
   const float* sample;
   float* prev;
-  const float* coef;   // device [2] = {cx, ce}
+  const float* coef;   // device [2] = {cx, ce}; with `seed`: [4] = {cx, ce, sigma, step (uint32 bits)}
+  const uint32_t* seed;  // optional device [2]: ancestral noise  prev += sigma * N(0, 1)[seed, step, element]
 };
 
 template <bool kSmemW>
@@ -302,7 +355,15 @@ __global__ void __launch_bounds__(256, kSmemW ? 2 : 4) conv_small_out_kernel(Sma
       const size_t base = static_cast<size_t>(b) * nout * hw + static_cast<size_t>(y) * p.W + x;
       for (int j = 0; j < nout; ++j) {
         if (p.out) p.out[base + j * hw] = o[j];
-        if (p.prev) p.prev[base + j * hw] = p.coef[0] * p.sample[base + j * hw] + p.coef[1] * o[j];
+        if (p.prev) {
+          float v = p.coef[0] * p.sample[base + j * hw] + p.coef[1] * o[j];
+          if (p.seed) {  // DDPMScheduler.step: + sqrt(variance) * noise (sigma = 0 at the last step)
+            const float sigma = p.coef[2];
+            if (sigma != 0.f)
+              v += sigma * philox_normal(p.seed[0], p.seed[1], __float_as_uint(p.coef[3]), base + j * hw);
+          }
+          p.prev[base + j * hw] = v;
+        }
       }
     }
   }
@@ -515,7 +576,7 @@ int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* 
 
 int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, const float* w, const float* bias,
                        int Cout, const float* w2, const float* b2, int Cout2, float* out, const float* sample,
-                       float* prev, const float* coef, void* stream) {
+                       float* prev, const float* coef, const uint32_t* seed, void* stream) {
   DFU_REQUIRE(Cout >= 1 && Cout <= 8 && Cin % 4 == 0 && (ksz == 1 || ksz == 3), "conv_small_out: Cout=%d Cin=%d", Cout,
               Cin);
   DFU_REQUIRE(!w2 || (Cout2 >= 1 && Cout2 <= 8), "conv_small_out: Cout2=%d", Cout2);
@@ -524,7 +585,7 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   SmallOut p;
   p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.ksz = ksz; p.Cout = Cout;
   p.w = w; p.bias = bias; p.w2 = w2; p.b2 = b2; p.Cout2 = Cout2; p.out = out;
-  p.sample = sample; p.prev = prev; p.coef = coef;
+  p.sample = sample; p.prev = prev; p.coef = coef; p.seed = seed;
   const long long npix = static_cast<long long>(B) * H * W;
   const size_t wbytes = static_cast<size_t>(Cout) * ksz * ksz * Cin * sizeof(float);
   // staging the weights pays only when a CTA then walks many pixels (VAE maps); the 64x64 UNet output conv keeps
@@ -543,6 +604,14 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
     DFU_CHECK_CUDA(launch_k(conv_small_out_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), wbytes, static_cast<cudaStream_t>(stream), p));
   else
     DFU_CHECK_CUDA(launch_k(conv_small_out_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+int dfu_philox_normal(uint64_t seed, uint32_t step, int64_t n, float* out, uint32_t* bits, void* stream) {
+  DFU_REQUIRE(n > 0 && (out || bits), "philox_normal: nothing to write");
+  philox_normal_kernel<<<ew_grid2(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), step, n, out, bits);
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -531,15 +531,26 @@ def pack_small_out_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def conv_small_out(x: torch.Tensor, wp: torch.Tensor, bias, out: Optional[torch.Tensor], *, w2=None, b2=None,
-                   sample=None, prev=None, coef=None):
-    """x [B,H,W,Cin] fp32 NHWC; wp packed [Cout, k*k, Cin]; out NCHW.  Optional fused 1x1 (w2,b2) / scheduler step."""
+                   sample=None, prev=None, coef=None, seed=None):
+    """x [B,H,W,Cin] fp32 NHWC; wp packed [Cout, k*k, Cin]; out NCHW.  Optional fused 1x1 (w2,b2) / scheduler step
+    (coef = device {cx, ce}; with seed = device int32 [2]: {cx, ce, sigma, step} and the ancestral noise is added)."""
     B, H, W, Cin = x.shape
     Cout, kk, _ = wp.shape
     ksz = 3 if kk == 9 else 1
     with _Prof('conv_small_out', 1):
         check(lib().dfu_conv_small_out(x.data_ptr(), B, H, W, Cin, ksz, wp.data_ptr(), _ptr(bias), Cout, _ptr(w2),
                                        _ptr(b2), 0 if w2 is None else w2.shape[0], _ptr(out), _ptr(sample), _ptr(prev),
-                                       _ptr(coef), _stream()), "dfu_conv_small_out")
+                                       _ptr(coef), _ptr(seed), _stream()), "dfu_conv_small_out")
+
+
+def philox_normal(seed: int, step: int, n: int, device="cuda", bits: bool = False):
+    """-> fp32 [n] N(0,1) of dfu_philox_normal (and, with bits=True, the raw Philox words int32 [n, 2])."""
+    out = torch.empty((n,), dtype=torch.float32, device=device)
+    raw = torch.empty((n, 2), dtype=torch.int32, device=device) if bits else None
+    with _Prof('philox_normal', 1):
+        check(lib().dfu_philox_normal(seed & 0xFFFFFFFFFFFFFFFF, step, n, out.data_ptr(), _ptr(raw), _stream()),
+              "dfu_philox_normal")
+    return (out, raw) if bits else out
 
 
 def axpbypcz(x, e, n, a: float, b: float, c: float, y):

@@ -75,7 +75,7 @@ class DiffUTEPipeline:
     @staticmethod
     def _tproj_offset(UB: int) -> int:
         """start of the time projections inside a step row, 16-byte aligned (the epilogues read them as float4)"""
-        return (UB + 2 + 3) // 4 * 4
+        return (UB + 4 + 3) // 4 * 4
 
     def _step_rows(self, ts, UB, fused, sched):
         """Per-step device rows [t x UB | cx, ce | time projections]: everything one step needs that depends on t only.
@@ -94,8 +94,11 @@ class DiffUTEPipeline:
             tv.fill_(float(t))
             rows[i, :UB] = float(t)
             if fused:
-                cx, ce = sched.collapsed_coefficients(t)
-                rows[i, UB], rows[i, UB + 1] = cx, ce
+                co = sched.collapsed_coefficients(t)   # DDIM: (cx, ce); DDPM: (cx, ce, sigma)
+                rows[i, UB], rows[i, UB + 1] = co[0], co[1]
+                if len(co) > 2:                          # ancestral: sigma and the step index (uint32 bits) of the noise stream
+                    rows[i, UB + 2] = co[2]
+                    rows[i, UB + 3:UB + 4].view(torch.int32)[0] = i
             self.unet.time_projections(tv, rows[i, off:].view(UB, TT))
         self._rows_cache[key] = rows
         return rows
@@ -114,7 +117,11 @@ class DiffUTEPipeline:
         ml = A.get("pipe.masked", (B, 4, h, w))
         off = self._tproj_offset(B)
         state = A.get("pipe.state", (off + self.unet.temb_total * B,))
-        step_io = (lat, lat, state[B:B + 2]) if fused else None
+        step_io = None
+        if fused == 1:
+            step_io = (lat, lat, state[B:B + 2])
+        elif fused == 2:  # DDPM: + the per-request noise seed (two 32-bit words, written once per call)
+            step_io = (lat, lat, state[B:B + 4], A.get("pipe.seed", (2,), torch.int32))
         tproj = state[off:].view(B, self.unet.temb_total)
 
         def run():
@@ -136,7 +143,7 @@ class DiffUTEPipeline:
                  guidance_scale: float = 1.0, negative_glyph_embeds: Optional[torch.Tensor] = None, eta: float = 0.0,
                  generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
                  posterior_noise: Optional[torch.Tensor] = None, sample_posterior: bool = True,
-                 output_type: str = "pt", return_dict: bool = True):
+                 output_type: str = "pt", return_dict: bool = True, noise_seed: Optional[int] = None):
         """image / masked_image [B,3,H,W] in [-1,1]; mask_image [B,1,H,W] (1 = region to rewrite);
         glyph_embeds [B,577,1024] (or `text` = glyph images for the attached TrOCR encoder).  Returns decoded RGB in
         [-1,1] for output_type "pt" (what vae.decode returns at app.ipynb:819), [0,1] HWC numpy for "np", PIL for
@@ -163,8 +170,15 @@ class DiffUTEPipeline:
         sf = float(self.vae.config["scaling_factor"])
         do_cfg = guidance_scale != 1.0 and negative_glyph_embeds is not None
         sched = self.scheduler
-        fused = (self.fuse_scheduler_step and isinstance(sched, DDIMScheduler) and eta == 0.0
-                 and not sched.config["clip_sample"] and not do_cfg)
+        # 1: DDIM update in conv_out's epilogue; 2: the ancestral DDPM update the reference runs (app.ipynb:545, :816) with
+        # its Gaussian noise generated in the same epilogue -- unless the caller supplies a torch generator, whose stream
+        # only torch can reproduce (then the step runs as its own kernel on torch.randn noise)
+        fused = 0
+        if self.fuse_scheduler_step and not sched.config["clip_sample"] and not do_cfg:
+            if isinstance(sched, DDIMScheduler) and eta == 0.0:
+                fused = 1
+            elif isinstance(sched, DDPMScheduler) and (generator is None or noise_seed is not None):
+                fused = 2
         UB = 2 * B if do_cfg else B
 
         # --- step-invariant work (once per request) -------------------------------------------------
@@ -200,6 +214,13 @@ class DiffUTEPipeline:
         # --- the loop (app.ipynb:806-816) -------------------------------------------------------------
         if fused:
             lat_buf.copy_(latents)
+            if fused == 2:
+                if noise_seed is None:  # from torch's default generator: torch.manual_seed makes the run reproducible
+                    noise_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                self.last_noise_seed = int(noise_seed)
+                words = [noise_seed & 0xFFFFFFFF, (noise_seed >> 32) & 0xFFFFFFFF]
+                A.get("pipe.seed", (2,), torch.int32).copy_(
+                    torch.tensor([w - (1 << 32) if w >= (1 << 31) else w for w in words], dtype=torch.int32))
             for i in range(len(ts)):
                 state.copy_(rows[i])       # one small D2D copy: timestep + DDIM coefficients of this step
                 graph.replay()             # UNet + scheduler update, latents advanced in place

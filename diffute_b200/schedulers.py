@@ -208,6 +208,13 @@ class DDPMScheduler(_SchedulerBase):
         sigma = math.sqrt(var) if t > 0 else 0.0
         return a0, a1, c0, c1, 0.0, sigma, bool(self.config["clip_sample"])
 
+    def collapsed_coefficients(self, t: int):
+        """(cx, ce, sigma) with prev = cx*x + ce*m + sigma*z when no clipping -- the fused conv_out epilogue's form."""
+        a0, a1, p0, d0, d1, sigma, clip = self.step_coefficients(t)
+        if clip:
+            raise ValueError("collapsed form needs clip_sample=False")
+        return p0 * a0 + d0, p0 * a1 + d1, sigma
+
     def step(self, model_output, timestep, sample, generator=None, return_dict: bool = True):
         t = _t_int(timestep)
         a0, a1, p0, d0, d1, sigma, clip = self.step_coefficients(t)

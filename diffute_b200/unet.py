@@ -492,8 +492,9 @@ class UNet2DConditionModel:
         if step_io is None:
             ops.conv_small_out(o32, w["conv_out.wp"], w["conv_out.b"], out)
         else:  # fused scheduler update: prev = coef[0]*latents + coef[1]*eps written by the same kernel
-            lat, prev, coef = step_io
-            ops.conv_small_out(o32, w["conv_out.wp"], w["conv_out.b"], out, sample=lat, prev=prev, coef=coef)
+            lat, prev, coef = step_io[:3]  # (+ seed words: the ancestral DDPM noise is added by the same kernel)
+            ops.conv_small_out(o32, w["conv_out.wp"], w["conv_out.b"], out, sample=lat, prev=prev, coef=coef,
+                               seed=step_io[3] if len(step_io) > 3 else None)
         return out
 
     def _run(self, B, H, W):

@@ -173,7 +173,13 @@ int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* 
  * prev = coef[0]*sample + coef[1]*result  (DDIMScheduler.step collapsed, app.ipynb:816 / SURVEY a12). */
 int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, const float* w, const float* bias,
                        int Cout, const float* w2, const float* b2, int Cout2, float* out, const float* sample,
-                       float* prev, const float* coef, void* stream);
+                       float* prev, const float* coef, const uint32_t* seed, void* stream);
+/* Gaussian noise as a pure function of (seed, step, element index): Philox4x32-10 keyed by `seed`, counter (index lo,
+ * index hi, step, 0), the first two output words -> 24-bit uniforms (k + 0.5) / 2^24 -> sqrt(-2 ln u1) cos(2 pi u2).
+ * This is the stream dfu_conv_small_out's fused ancestral step adds (`seed` != NULL: coef = {cx, ce, sigma, step};
+ * prev = cx * sample + ce * eps + sigma * z[element], DDPMScheduler.step at app.ipynb:816).  out [n] and / or the raw
+ * words bits [n][2]. */
+int dfu_philox_normal(uint64_t seed, uint32_t step, int64_t n, float* out, uint32_t* bits, void* stream);
 /* y = a*x + b*e (+ c*n): scheduler.step / add_noise / get_velocity in collapsed-coefficient form. */
 int dfu_axpbypcz(const float* x, const float* e, const float* n, float a, float b, float c, float* y,
                  int64_t total, void* stream);

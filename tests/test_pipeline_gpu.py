@@ -238,3 +238,55 @@ def test_from_pretrained_folder_and_ddpm_reference_path(world, tmp_path):
     err = _rel(out, ref)
     print(f"DDPM 4-step loop (reference sampler): decoded RGB maxrel {err:.3e}")
     assert err < 1e-3, err
+
+
+def test_ancestral_ddpm_fused_with_in_kernel_noise(world):
+    """The sampler the reference runs (DDPMScheduler.step without a generator, app.ipynb:545 / :816) as ONE captured
+    graph per step: the posterior mean and sqrt(variance) * z are written by conv_out's epilogue, z from the kernel's
+    counter-based Philox stream.  Oracle: the same loop on the CPU with z restated by oracle/philox.py."""
+    import numpy as np
+    import torch.nn.functional as F
+    from diffute_b200 import ops, synthetic
+    from diffute_b200.pipeline import DiffUTEPipeline
+    from diffute_b200.schedulers import DDPMScheduler
+    from oracle import DDPMOracle, philox
+    usd, vsd, uo, vo = world
+    # the noise stream itself: raw Philox words bit for bit, Gaussians to float rounding of log / cos
+    z, bits = ops.philox_normal(0x123456789ABCDEF, 5, 70000, bits=True)
+    zr, br = philox.normal(0x123456789ABCDEF, 5, 70000, return_bits=True)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), br)
+    assert np.abs(z.cpu().numpy() - zr).max() < 5e-6
+    pipe = DiffUTEPipeline.from_synthetic("fp16x2", "fp16x2", state_dicts=(usd, vsd))
+    pipe.scheduler = DDPMScheduler()
+    steps, px, seed = 6, 128, 987654321012345
+    inp = synthetic.make_inputs(2, px, px)
+    kw = dict(masked_image=inp["masked_image"], mask_image=inp["mask"], glyph_embeds=inp["glyph_embeds"],
+              latents=inp["latents"], posterior_noise=inp["posterior_noise"], num_inference_steps=steps)
+    launches0 = ops.gemm_stats()["launches"]
+    out = pipe(**kw, noise_seed=seed)
+    assert pipe.last_noise_seed == seed
+    o = DDPMOracle()
+    o.set_timesteps(steps)
+    mask_l = F.interpolate(inp["mask"], size=(px // 8, px // 8))
+    ml = vo.encode(inp["masked_image"]).latent_dist.sample(noise=inp["posterior_noise"]) * 0.18215
+    lat = inp["latents"].clone()
+    for i, t in enumerate(o.timesteps):
+        eps = uo(torch.cat([lat, mask_l, ml], 1), t, inp["glyph_embeds"]).sample
+        noise = torch.from_numpy(philox.normal(seed, i, lat.numel())).view_as(lat)
+        lat = o.step(eps, t, lat, noise=noise).prev_sample
+    ref = vo.decode(lat / 0.18215).sample
+    err = _rel(out.images, ref)
+    print(f"fused ancestral DDPM, {steps} steps at {px}px, batch 2: decoded RGB maxrel {err:.3e}")
+    assert err < 1e-3, err
+    # reproducible from the seed, different with another one, and seeded by torch's default generator otherwise
+    again = pipe(**kw, noise_seed=seed).images
+    assert torch.equal(again, out.images)
+    other = pipe(**kw, noise_seed=seed + 1).images
+    assert not torch.equal(other, out.images)
+    torch.manual_seed(11)
+    a = pipe(**kw).images
+    s1 = pipe.last_noise_seed
+    torch.manual_seed(11)
+    b = pipe(**kw).images
+    assert pipe.last_noise_seed == s1 and torch.equal(a, b)
+    assert ops.gemm_stats()["launches"] > launches0
