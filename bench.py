@@ -335,6 +335,33 @@ def extra_configs(pipe, dev, peaks):
         "roofline": {"bound": "tensor", "achieved": step_tf, "peak": tf, "unit": "TFLOP/s", "frac": step_tf / tf,
                      "what": "whole UNet step at UNet-batch 8, 96x96 latents: algorithmic FLOP / graph-replay time",
                      "per_layer_roofline_ms": 11.422, "frac_of_per_layer_roofline": 11.422 / step_ms}}
+    del d
+
+    # ---- the reference's own serving call: text_editing(photo, box) with ITS sampler (ancestral DDPM), uint8 in / out --
+    import numpy as np
+    from diffute_b200 import glue
+    from diffute_b200.schedulers import DDIMScheduler, DDPMScheduler
+    photo = np.random.default_rng(5).integers(0, 256, (1080, 1440, 3), dtype=np.uint8)   # host memory, like cv2.imread
+    box = (500, 400, 860, 470)
+    emb = dev_inputs(1, PX)["glyph_embeds"]
+    ddim = pipe.scheduler
+    try:
+        pipe.scheduler = DDPMScheduler(**{k: v for k, v in ddim.config.items() if k in DDPMScheduler._defaults})
+        call = lambda: glue.text_editing(pipe, None, photo, NSTEPS, *box, glyph_embeds=emb, noise_seed=1)
+        ms = _median_call_ms(call, warmup=2, n=3)
+        pre = glue.preprocess(photo, box, device=dev)
+        t_pre = _event_ms(lambda: glue.preprocess(photo, box, device=dev), 5)
+        dec = torch.zeros((1, 3, PX, PX), device=dev)
+        t_post = _event_ms(lambda: glue.composite(dec, pre).cpu(), 5)
+    finally:
+        pipe.scheduler = ddim
+    out["text_editing_ddpm"] = {
+        "workload": "reference serving call text_editing (app.ipynb:653-856): 1440x1080 uint8 photograph on the host -> crop "
+                    "window / mask / resize / normalise on the GPU -> 50 ancestral DDPM steps (the reference's sampler, noise "
+                    "generated in conv_out's epilogue) -> decode -> resize + paste on the GPU -> uint8 photograph on the host",
+        "images_per_s": 1.0 / (ms / 1e3), "ms_per_image": ms,
+        "preprocess_ms_incl_h2d": t_pre, "composite_ms_incl_d2h": t_post,
+        "h2d_bytes": int(photo.nbytes), "d2h_bytes": int(photo.nbytes)}
     return out
 
 
