@@ -7,6 +7,8 @@ modules that chenhaoxing/DiffUTE calls on its sampling path
     UNet2DConditionModel.forward      -> oracle.unet.UNetOracle
     AutoencoderKL.encode/decode       -> oracle.vae.VAEOracle
     DDIMScheduler / DDPMScheduler     -> oracle.schedulers
+    text_editing's cv2 / PIL / numpy glue (app.ipynb:663-771, :821-841) -> oracle.glue  (pinned to cv2 4.13 / PIL)
+    the ancestral step's Gaussian noise stream                          -> oracle.philox (Random123 known answers)
 
 diffusers itself is not vendored under /root/reference, is not pinned by the
 reference (requirements.txt:1-8; floor "0.15.0.dev0" at train_diffute_v1.py:63)
