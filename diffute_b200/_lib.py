@@ -107,6 +107,8 @@ SIGNATURES = {
     "dfu_conv_small_out": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dfu_philox_normal": (_i, [C.c_uint64, C.c_uint32, _i64, _vp, _vp, _vp]),
     "dfu_glue_preprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "dfu_glyph_preprocess_workspace": (_sz, [_i, _i, _i]),
+    "dfu_glyph_preprocess": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "dfu_glue_composite": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dfu_axpbypcz": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64, _vp]),
     "dfu_scheduler_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _i64, _vp]),

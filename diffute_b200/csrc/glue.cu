@@ -22,7 +22,8 @@ struct U8Coef {
 
 // cv::resize INTER_LINEAR coefficient of destination index d (resize.cpp: fx = (float)((dx + 0.5) * scale_x - 0.5))
 __device__ __forceinline__ U8Coef coef_u8(int d, int ssize, double scale, bool horizontal) {
-  float f = static_cast<float>((static_cast<double>(d) + 0.5) * scale - 0.5);
+  // (explicit round-to-nearest steps: no contraction into a double-precision fma, which the host code does not do)
+  float f = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(d), 0.5), scale), 0.5));
   int s = static_cast<int>(floorf(f));
   f = __fsub_rn(f, static_cast<float>(s));
   if (horizontal) {
@@ -152,8 +153,8 @@ __global__ void __launch_bounds__(256) glue_composite_kernel(const CompParams p)
     return;
   }
   // cv2.resize float32: the fraction is taken in double precision
-  const double fxd = (static_cast<double>(dx) + 0.5) * p.scale_x - 0.5;
-  const double fyd = (static_cast<double>(dy) + 0.5) * p.scale_y - 0.5;
+  const double fxd = __dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dx), 0.5), p.scale_x), 0.5);
+  const double fyd = __dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dy), 0.5), p.scale_y), 0.5);
   int sx = static_cast<int>(floor(fxd)), sy = static_cast<int>(floor(fyd));
   float fx = static_cast<float>(fxd - static_cast<double>(sx));
   const float fy = static_cast<float>(fyd - static_cast<double>(sy));
@@ -248,6 +249,140 @@ extern "C" int dfu_glue_composite(const float* decoded, int S, const uint8_t* im
   p.out = out;
   dim3 grid((w + 255) / 256, h);
   glue_composite_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DFU_CHECK_CUDA(cudaGetLastError());
+  return DFU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TrOCRProcessor's image side (app.ipynb:773-774: processor(images=[draw_ttf]).pixel_values) = ViTImageProcessor:
+// PIL Image.resize((S, S), BILINEAR) -> * 1/255 -> (x - 0.5) / 0.5 -> CHW float32.  Pillow's resample (Resample.c) is
+// an antialiased separable filter: triangle of support max(scale, 1), weights computed in double, normalised, turned
+// into 22-bit fixed point (int)(0.5 + w * 2^22), horizontal pass first with a uint8 intermediate (clip8), then the
+// vertical pass.  Reproduced bit for bit (oracle/glue.py::pil_resize_bilinear, pinned against Pillow and against
+// transformers' ViTImageProcessor); the double-precision steps use explicit round-to-nearest intrinsics so that no
+// multiply-add is contracted.
+// ---------------------------------------------------------------------------------------------
+namespace dfu {
+
+constexpr int kPilBits = 22;
+
+__device__ __forceinline__ double pil_triangle(double x) {
+  if (x < 0.0) x = -x;
+  return x < 1.0 ? __dsub_rn(1.0, x) : 0.0;
+}
+
+// one thread per destination index: coefficient row K[xx][ksize] and bounds B[xx] = (first source index, count)
+__global__ void pil_coeffs_kernel(int in_size, int out_size, int ksize, int* __restrict__ K, int* __restrict__ B) {
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xx >= out_size) return;
+  const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  const double support = fs;  // bilinear: filter support 1.0 x filterscale
+  const double ss = __ddiv_rn(1.0, fs);
+  const double center = __dmul_rn(__dadd_rn(static_cast<double>(xx), 0.5), scale);
+  int xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  auto weight = [&](int x) {
+    return pil_triangle(__dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss));
+  };
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) ww = __dadd_rn(ww, weight(x));
+  int* k = K + static_cast<size_t>(xx) * ksize;
+  for (int x = 0; x < ksize; ++x) {
+    double w = x < xmax ? weight(x) : 0.0;
+    if (x < xmax && ww != 0.0) w = __ddiv_rn(w, ww);
+    k[x] = static_cast<int>(__dadd_rn(0.5, __dmul_rn(w, static_cast<double>(1 << kPilBits))));
+  }
+  B[2 * xx] = xmin;
+  B[2 * xx + 1] = xmax;
+}
+
+__device__ __forceinline__ int clip8(int v) {
+  v >>= kPilBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__global__ void __launch_bounds__(256)
+pil_resize_normalize_kernel(const uint8_t* __restrict__ img, int h, int w, int S, const int* __restrict__ Kx,
+                            const int* __restrict__ Bx, int ksx, const int* __restrict__ Ky, const int* __restrict__ By,
+                            int ksy, float* __restrict__ out) {
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yy = blockIdx.y;
+  if (xx >= S) return;
+  const bool need_h = w != S, need_v = h != S;  // Pillow skips a pass whose size does not change
+  const int xmin = need_h ? Bx[2 * xx] : xx, xcnt = need_h ? Bx[2 * xx + 1] : 1;
+  const int ymin = need_v ? By[2 * yy] : yy, ycnt = need_v ? By[2 * yy + 1] : 1;
+  const int* kx = Kx + static_cast<size_t>(xx) * ksx;
+  const int* ky = Ky + static_cast<size_t>(yy) * ksy;
+  int acc[3] = {1 << (kPilBits - 1), 1 << (kPilBits - 1), 1 << (kPilBits - 1)};
+  int last[3] = {0, 0, 0};
+  for (int ty = 0; ty < ycnt; ++ty) {
+    const uint8_t* row = img + (static_cast<size_t>(ymin + ty) * w + xmin) * 3;
+    int hs[3];
+    if (need_h) {
+      hs[0] = hs[1] = hs[2] = 1 << (kPilBits - 1);
+      for (int tx = 0; tx < xcnt; ++tx) {
+        const int k = kx[tx];
+        hs[0] += row[tx * 3] * k;
+        hs[1] += row[tx * 3 + 1] * k;
+        hs[2] += row[tx * 3 + 2] * k;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hs[c] = clip8(hs[c]);  // the horizontal pass writes a uint8 image
+    } else {
+      hs[0] = row[0];
+      hs[1] = row[1];
+      hs[2] = row[2];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      last[c] = hs[c];
+      if (need_v) acc[c] += hs[c] * ky[ty];
+    }
+  }
+  const size_t plane = static_cast<size_t>(S) * S;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int v = need_v ? clip8(acc[c]) : last[c];
+    // transformers' PIL / numpy backend: rescale = float32(float64(x) * (1 / 255)), normalize = (x - 0.5) / 0.5 in float32
+    const float x = static_cast<float>(__dmul_rn(static_cast<double>(v), 1.0 / 255.0));
+    out[c * plane + static_cast<size_t>(yy) * S + xx] = __fdiv_rn(__fsub_rn(x, 0.5f), 0.5f);
+  }
+}
+
+__host__ inline int pil_ksize(int in_size, int out_size) {
+  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  const double support = scale < 1.0 ? 1.0 : scale;
+  return static_cast<int>(ceil(support)) * 2 + 1;
+}
+
+}  // namespace dfu
+
+extern "C" size_t dfu_glyph_preprocess_workspace(int h, int w, int out_size) {
+  using namespace dfu;
+  if (h <= 0 || w <= 0 || out_size <= 0) return 0;
+  return static_cast<size_t>(out_size) * (pil_ksize(w, out_size) + pil_ksize(h, out_size) + 4) * sizeof(int);
+}
+
+extern "C" int dfu_glyph_preprocess(const uint8_t* image, int h, int w, int out_size, void* workspace,
+                                    size_t workspace_bytes, float* out, void* stream) {
+  using namespace dfu;
+  DFU_REQUIRE(image && out && h > 0 && w > 0 && out_size > 0, "glyph_preprocess: bad arguments");
+  const size_t need = dfu_glyph_preprocess_workspace(h, w, out_size);
+  DFU_REQUIRE(workspace && workspace_bytes >= need, "glyph_preprocess: workspace %zu < %zu bytes", workspace_bytes, need);
+  const int S = out_size, ksx = pil_ksize(w, S), ksy = pil_ksize(h, S);
+  int* Kx = static_cast<int*>(workspace);
+  int* Bx = Kx + static_cast<size_t>(S) * ksx;
+  int* Ky = Bx + 2 * S;
+  int* By = Ky + static_cast<size_t>(S) * ksy;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pil_coeffs_kernel<<<(S + 127) / 128, 128, 0, st>>>(w, S, ksx, Kx, Bx);
+  pil_coeffs_kernel<<<(S + 127) / 128, 128, 0, st>>>(h, S, ksy, Ky, By);
+  dim3 grid((S + 255) / 256, S);
+  pil_resize_normalize_kernel<<<grid, 256, 0, st>>>(image, h, w, S, Kx, Bx, ksx, Ky, By, ksy, out);
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }

@@ -194,3 +194,40 @@ class TrOCRGlyphEncoder:
         return GlyphEncoderOutput(out) if return_dict else (out,)
 
     __call__ = forward
+
+
+class _ProcessorOutput(dict):
+    """BatchFeature-like: `.pixel_values` and `["pixel_values"]`."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class TrOCRGlyphProcessor:
+    """Image side of `TrOCRProcessor` (app.ipynb:546, 773-774: `processor(images=ttf_imgs, return_tensors="pt")
+    .pixel_values`) on the GPU: each uint8 glyph image goes to the device once and `dfu_glyph_preprocess` produces its
+    [3, 384, 384] slice of `pixel_values` -- PIL's antialiased bilinear resize, rescale 1/255 and normalise 0.5 / 0.5,
+    bit-identical to transformers' PIL-backend ViTImageProcessor (trocr-large-printed's preprocessor_config.json:
+    size 384, resample 2, image_mean = image_std = 0.5).  The text side (tokenizer) is not on the sampling path."""
+
+    def __init__(self, size: int = 384, device="cuda"):
+        self.size, self.device = int(size), torch.device(device)
+
+    def __call__(self, images, return_tensors: str = "pt", **unused):
+        import numpy as np
+        if return_tensors != "pt":
+            raise NotImplementedError("return_tensors='pt' only")
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        out = torch.empty((len(images), 3, self.size, self.size), dtype=torch.float32, device=self.device)
+        for i, im in enumerate(images):
+            a = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(im)))
+            if a.dim() == 2:  # PIL 'L' image: ViTImageProcessor converts to RGB
+                a = a[:, :, None].expand(-1, -1, 3)
+            if a.dtype != torch.uint8 or a.dim() != 3 or a.shape[2] != 3:
+                raise ValueError("glyph images must be uint8 [h, w, 3] (PIL RGB image, numpy array or tensor)")
+            ops.glyph_preprocess(a.to(self.device).contiguous(), out[i])
+        return _ProcessorOutput(pixel_values=out)

@@ -460,6 +460,20 @@ def glue_preprocess(image_u8: torch.Tensor, window, bbox, out_size: int = 512, l
     return img, msk_img, mask, mask_lat
 
 
+def glyph_preprocess(image_u8: torch.Tensor, out: torch.Tensor):
+    """image_u8 uint8 [h, w, 3] on the device -> out fp32 [3, S, S]: ViTImageProcessor (PIL bilinear resize to S x S,
+    rescale 1/255, normalise 0.5 / 0.5), dfu_glyph_preprocess."""
+    h, w, c = image_u8.shape
+    S = out.shape[-1]
+    assert c == 3 and image_u8.dtype == torch.uint8 and image_u8.is_contiguous() and out.shape == (3, S, S)
+    need = lib().dfu_glyph_preprocess_workspace(h, w, S)
+    ws = torch.empty((need,), dtype=torch.uint8, device=image_u8.device)
+    with _Prof("glyph_preprocess", 3):
+        check(lib().dfu_glyph_preprocess(image_u8.data_ptr(), h, w, S, ws.data_ptr(), need, out.data_ptr(), _stream()),
+              "dfu_glyph_preprocess")
+    return out
+
+
 def glue_composite(decoded: torch.Tensor, image_u8: torch.Tensor, origin, size, bbox, wrap: bool = False) -> torch.Tensor:
     """decoded fp32 [3, S, S] in [-1, 1]; image_u8 uint8 [h, w, 3]; origin = (x_s, y_s), size = (r_w, r_h) of the pasted
     region; bbox = numpy-slice corners (end exclusive).  -> uint8 [h, w, 3] (dfu_glue_composite)."""

@@ -64,8 +64,9 @@ class DiffUTEPipeline:
 
     # ------------------------------------------------------------------------------------------
     def encode_glyph(self, glyph_images):
-        """TrOCR encoder last_hidden_state [B,577,1024] (app.ipynb:773-776).  Runs stock transformers: the glyph
-        encoder is outside the hot path (once per request, ~1% of the FLOPs; SURVEY 2.1 #5 / 8f f3)."""
+        """TrOCR encoder last_hidden_state [B,577,1024] (app.ipynb:773-776) through the attached `glyph_processor` /
+        `glyph_encoder`: glyph_encoder.TrOCRGlyphProcessor + TrOCRGlyphEncoder (native kernels), or transformers' own
+        objects -- both have the same call signatures.  Once per request, ~1% of the FLOPs (SURVEY 2.1 #5 / 8f f3)."""
         if self.glyph_encoder is None or self.glyph_processor is None:
             raise ValueError("no glyph encoder attached: pass glyph_embeds [B,577,1024] instead of text/glyph images")
         pv = self.glyph_processor(images=glyph_images, return_tensors="pt").pixel_values.to(self.device)

@@ -217,6 +217,13 @@ int dfu_glue_preprocess(const uint8_t* image, int h, int w, int x_s, int y_s, in
 int dfu_glue_composite(const float* decoded, int S, const uint8_t* image, int h, int w, int x_s, int y_s, int r_w,
                        int r_h, int bx0, int by0, int bx1, int by1, int wrap, uint8_t* out, void* stream);
 
+/* TrOCRProcessor's image side (app.ipynb:773-774) = ViTImageProcessor: uint8 HWC glyph image [h][w][3] -> PIL
+ * Image.resize((S, S), BILINEAR) (Pillow's antialiased 22-bit fixed-point resample, bit-exact) -> * 1/255 ->
+ * (x - 0.5) / 0.5 -> out [3][S][S] fp32 (one sample of `pixel_values`).  workspace: coefficient tables. */
+size_t dfu_glyph_preprocess_workspace(int h, int w, int out_size);
+int dfu_glyph_preprocess(const uint8_t* image, int h, int w, int out_size, void* workspace, size_t workspace_bytes,
+                         float* out, void* stream);
+
 /* ---- fused attention core (head dim 64) --------------------------------------------------------
  * out[b, q, h*64:(h+1)*64] = softmax(Q_h K_h^T * scale) V_h for every sample b and head h: diffusers `Attention`
  * core of BasicTransformerBlock.attn1 (self, Nk = Nq = H*W) and attn2 (cross, Nk = 577 glyph tokens), SURVEY A.1,

@@ -29,7 +29,15 @@ CASES_F32 = [(21, (300, 300)), (22, (640, 640)), (23, (1000, 784)), (24, (256, 2
              (27, (3, 5))]
 CASES_RECT = [((40, 30), (5, 6, 20, 17)), ((40, 30), (0, 0, 39, 29)), ((40, 30), (-3, 10, 12, 50)), ((16, 16), (7, 7, 7, 7))]
 
-out = {"cv2": cv2.__version__, "u8": [], "f32": [], "rect": []}
+CASES_PIL = [(31, (60, 280, 3), (384, 384)), (32, (60, 640, 3), (384, 384)), (33, (60, 1500, 3), (384, 384)),
+             (34, (384, 200, 3), (384, 384)), (35, (500, 384, 3), (384, 384)), (36, (7, 5, 3), (33, 21)), (37, (384, 384, 3), (384, 384))]
+
+import PIL
+out = {"cv2": cv2.__version__, "pil": PIL.__version__, "u8": [], "f32": [], "rect": [], "pil_bilinear": []}
+for seed, shape, (ow, oh) in CASES_PIL:
+    src = u8_src(seed, shape, False)
+    out["pil_bilinear"].append({"seed": seed, "shape": list(shape), "dsize": [ow, oh],
+                                "sha256": sha(np.array(Image.fromarray(src).resize((ow, oh), resample=Image.BILINEAR)))})
 for seed, shape, (dw, dh), binary in CASES_U8:
     src = u8_src(seed, shape, binary)
     out["u8"].append({"seed": seed, "shape": list(shape), "dsize": [dw, dh], "binary": binary,
@@ -43,4 +51,4 @@ for (w, h), box in CASES_RECT:
     out["rect"].append({"size": [w, h], "box": list(box), "sha256": sha(np.array(m))})
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "glue_golden.json"), "w") as f:
     json.dump(out, f, indent=1)
-print("wrote", len(out["u8"]), len(out["f32"]), len(out["rect"]))
+print("wrote", len(out["u8"]), len(out["f32"]), len(out["rect"]), len(out["pil_bilinear"]))

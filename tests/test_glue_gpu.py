@@ -109,3 +109,17 @@ def test_text_editing_end_to_end(mods):
     diff = np.abs(edited.astype(int) - ref.astype(int))
     print(f"text_editing vs oracle chain: pixels differing {(diff > 0).mean():.2e}, max |diff| {diff.max()}")
     assert diff.max() <= 1 and (diff > 0).mean() < 2e-3   # decoded RGB agrees to ~1e-5: only rounding ties move
+
+
+@pytest.mark.parametrize("h,w", [(60, 200), (60, 680), (60, 1240), (384, 384), (500, 384), (384, 200), (7, 5)])
+def test_glyph_processor_bit_exact(mods, h, w):
+    """TrOCRProcessor's image side (app.ipynb:773-774) on the GPU == the numpy restatement of PIL's resample + the
+    PIL-backend ViTImageProcessor arithmetic (pinned to Pillow / transformers in tests/test_glue_oracle.py)."""
+    glue, G = mods
+    from diffute_b200.glyph_encoder import TrOCRGlyphProcessor
+    rng = np.random.default_rng(h * 13 + w)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(2)]
+    pv = TrOCRGlyphProcessor()(images=imgs, return_tensors="pt").pixel_values
+    assert pv.shape == (2, 3, 384, 384) and pv.dtype == torch.float32
+    for i, im in enumerate(imgs):
+        assert np.array_equal(pv[i].cpu().numpy(), G.vit_pixel_values(im)), (h, w, i)
