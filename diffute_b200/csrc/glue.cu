@@ -139,19 +139,11 @@ struct CompParams {
   uint8_t* out;  // [h][w][3]
 };
 
-__global__ void __launch_bounds__(256) glue_composite_kernel(const CompParams p) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
-  if (x >= p.w) return;
-  const size_t o = (static_cast<size_t>(y) * p.w + x) * 3;
+// value of output byte (y, x, c): the photograph's, or inside the pasted text box the resized decoded image
+__device__ __forceinline__ uint8_t composite_byte(const CompParams& p, int y, int x, int c, size_t o) {
   const int dx = x - p.x_s, dy = y - p.y_s;
   const bool inside = x >= p.bx0 && x < p.bx1 && y >= p.by0 && y < p.by1 && dx >= 0 && dx < p.r_w && dy >= 0 && dy < p.r_h;
-  if (!inside) {
-    p.out[o] = p.image[o];
-    p.out[o + 1] = p.image[o + 1];
-    p.out[o + 2] = p.image[o + 2];
-    return;
-  }
+  if (!inside) return p.image[o];
   // cv2.resize float32: the fraction is taken in double precision
   const double fxd = __dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dx), 0.5), p.scale_x), 0.5);
   const double fyd = __dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dy), 0.5), p.scale_y), 0.5);
@@ -168,20 +160,38 @@ __global__ void __launch_bounds__(256) glue_composite_kernel(const CompParams p)
   }
   const int x0 = sx, x1 = min(sx + 1, p.S - 1);
   const int y0 = min(max(sy, 0), p.S - 1), y1 = min(max(sy + 1, 0), p.S - 1);
-  const size_t plane = static_cast<size_t>(p.S) * p.S;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* d = p.decoded + c * plane;
-    auto px = [&](int yy, int xx) {  // image = (image_vae / 2 + 0.5) * 255.0 in float32 (app.ipynb:822)
-      return __fmul_rn(__fadd_rn(__fmul_rn(d[static_cast<size_t>(yy) * p.S + xx], 0.5f), 0.5f), 255.0f);
-    };
-    const float v00 = px(y0, x0), v01 = px(y0, x1), v10 = px(y1, x0), v11 = px(y1, x1);
-    const float r0 = __fmaf_rn(__fsub_rn(v01, v00), fx, v00);
-    const float r1 = __fmaf_rn(__fsub_rn(v11, v10), fx, v10);
-    const float v = __fmaf_rn(__fsub_rn(r1, r0), fy, r0);
-    int q = __float2int_rn(v);  // np.round: half to even
-    q = p.wrap ? (q & 255) : (q < 0 ? 0 : (q > 255 ? 255 : q));
-    p.out[o + c] = static_cast<uint8_t>(q);
+  const float* d = p.decoded + static_cast<size_t>(c) * p.S * p.S;
+  auto px = [&](int yy, int xx) {  // image = (image_vae / 2 + 0.5) * 255.0 in float32 (app.ipynb:822)
+    return __fmul_rn(__fadd_rn(__fmul_rn(d[static_cast<size_t>(yy) * p.S + xx], 0.5f), 0.5f), 255.0f);
+  };
+  const float v00 = px(y0, x0), v01 = px(y0, x1), v10 = px(y1, x0), v11 = px(y1, x1);
+  const float r0 = __fmaf_rn(__fsub_rn(v01, v00), fx, v00);
+  const float r1 = __fmaf_rn(__fsub_rn(v11, v10), fx, v10);
+  const float v = __fmaf_rn(__fsub_rn(r1, r0), fy, r0);
+  int q = __float2int_rn(v);  // np.round: half to even
+  q = p.wrap ? (q & 255) : (q < 0 ? 0 : (q > 255 ? 255 : q));
+  return static_cast<uint8_t>(q);
+}
+
+// One thread per 4 output bytes of the flattened [h][w][3] image: rows that the text box does not touch (nearly all of
+// the photograph) are copied as 32-bit words, coalesced; only words with a byte inside the box take the per-byte path.
+__global__ void __launch_bounds__(256) glue_composite_kernel(const CompParams p) {
+  const size_t total = static_cast<size_t>(p.h) * p.w * 3;
+  const size_t o = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (o >= total) return;
+  const size_t row_bytes = static_cast<size_t>(p.w) * 3;
+  const int y_first = static_cast<int>(o / row_bytes);
+  const int y_last = static_cast<int>(min(o + 3, total - 1) / row_bytes);
+  const bool rows_hit = y_last >= p.by0 && y_first < p.by1;  // (conservative) some byte may lie in the box's rows
+  if (!rows_hit && o + 4 <= total) {
+    *reinterpret_cast<uint32_t*>(p.out + o) = *reinterpret_cast<const uint32_t*>(p.image + o);
+    return;
+  }
+  for (int k = 0; k < 4 && o + k < total; ++k) {
+    const size_t b = o + k;
+    const int y = static_cast<int>(b / row_bytes);
+    const int rem = static_cast<int>(b - static_cast<size_t>(y) * row_bytes);
+    p.out[b] = composite_byte(p, y, rem / 3, rem % 3, b);
   }
 }
 
@@ -247,8 +257,8 @@ extern "C" int dfu_glue_composite(const float* decoded, int S, const uint8_t* im
   p.scale_x = 1.0 / (static_cast<double>(r_w) / static_cast<double>(S));
   p.scale_y = 1.0 / (static_cast<double>(r_h) / static_cast<double>(S));
   p.out = out;
-  dim3 grid((w + 255) / 256, h);
-  glue_composite_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const size_t words = (static_cast<size_t>(h) * w * 3 + 3) / 4;
+  glue_composite_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
