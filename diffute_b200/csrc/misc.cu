@@ -2,6 +2,7 @@
 // (time-embedding MLP and the 22 time_emb_proj layers in one launch), the few-channel edge convolutions
 // (conv_in 9->320, conv_out 320->4 with the scheduler step fused, VAE 3->128 / 128->3 / 4->512 / 512->8 and the
 // 1x1 quant convs), row softmax for the single-head VAE attention and the scheduler updates.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -371,6 +372,95 @@ __global__ void __launch_bounds__(256, kSmemW ? 2 : 4) conv_small_out_kernel(Sma
 }
 
 // ---------------------------------------------------------------------------------------------
+// The UNet's conv_out (3x3, Cout = 4) register-blocked: a warp owns FOUR consecutive pixels of a row, a lane owns channel
+// quads q = lane, lane + 32, ...; per input row it loads the six columns the four pixels' three horizontal taps touch
+// (6 x LDG.128) and the 12 weight quads (LDS.128 from the CTA's shared copy) for 192 FMAs -- the one-pixel-per-warp
+// kernel above issues a load per 4-16 FMAs and ran at 8 % of the fp32 peak (125 us at batch 8).  The 16 per-lane partial
+// sums (4 pixels x 4 outputs) are reduced across the warp by halving (16 shuffles instead of 80).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
+  pdl_trigger();
+  DFU_TR_BEGIN(TR_CONV_OUT);
+  extern __shared__ __align__(16) float sw[];  // [4][9][Cin]
+  const int C4 = p.Cin >> 2;
+  for (int i = threadIdx.x; i < 36 * C4; i += blockDim.x)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+  __syncthreads();
+  pdl_wait();
+  DFU_TR_MARK(6);
+  const int lane = threadIdx.x & 31;
+  const int W4 = p.W >> 2;
+  const int ngroups = p.B * p.H * W4;
+  const int nwarps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
+  const size_t hw = static_cast<size_t>(p.H) * p.W;
+  for (int grp = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5); grp < ngroups; grp += nwarps) {
+    const int x0 = (grp % W4) * 4;
+    const int yb = grp / W4;
+    const int y = yb % p.H;
+    const int b = yb / p.H;
+    float acc[16];  // [pixel][output]
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int q = lane; q < C4; q += 32) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+        if (iy < 0 || iy >= p.H) continue;  // (warp-uniform)
+        const float4* row = reinterpret_cast<const float4*>(p.x + (static_cast<size_t>(b) * p.H + iy) * p.W * p.Cin) + q;
+        float4 in[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const int ix = x0 - 1 + c;
+          in[c] = (ix >= 0 && ix < p.W) ? row[static_cast<size_t>(ix) * C4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int co = 0; co < 4; ++co) {
+            const float4 wv = *(reinterpret_cast<const float4*>(sw + (co * 9 + ky * 3 + kx) * p.Cin) + q);
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              const float4 v = in[px + kx];
+              acc[px * 4 + co] += wv.x * v.x + wv.y * v.y + wv.z * v.z + wv.w * v.w;
+            }
+          }
+        }
+      }
+    }
+    // reduction by halving: after the steps with masks 16, 8, 4, 2 a lane holds ONE of the 16 sums over its half / quarter /
+    // ... of the warp, index ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    // the last step adds the neighbouring lane
+#pragma unroll
+    for (int n = 8, m = 16; n >= 1; n >>= 1, m >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const float keep = up ? acc[i + n] : acc[i];
+        const float send = up ? acc[i] : acc[i + n];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+    const float total = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    if ((lane & 1) == 0) {
+      const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      const int px = idx >> 2, co = idx & 3;
+      const float o = total + (p.bias ? p.bias[co] : 0.f);
+      const size_t base = (static_cast<size_t>(b) * 4 + co) * hw + static_cast<size_t>(y) * p.W + x0 + px;
+      if (p.out) p.out[base] = o;
+      if (p.prev) {
+        float v = p.coef[0] * p.sample[base] + p.coef[1] * o;
+        if (p.seed) {
+          const float sigma = p.coef[2];
+          if (sigma != 0.f) v += sigma * philox_normal(p.seed[0], p.seed[1], __float_as_uint(p.coef[3]), base);
+        }
+        p.prev[base] = v;
+      }
+    }
+  }
+  DFU_TR_END();
+}
+
+// ---------------------------------------------------------------------------------------------
 // elementwise: y = a*x + b*e (+ c*n)   (DDIM eta=0: c = 0;  DDPM: x0/x form pre-collapsed on the host)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -590,9 +680,25 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   const size_t wbytes = static_cast<size_t>(Cout) * ksz * ksz * Cin * sizeof(float);
   // staging the weights pays only when a CTA then walks many pixels (VAE maps); the 64x64 UNet output conv keeps
   // one warp per pixel reading the weights through L1 (measured 11 us vs 19 us with the 46 KB copy per CTA)
-  const int w_in_smem = wbytes <= 200 * 1024 && npix >= 64LL * 8 * (num_sms() > 0 ? num_sms() : 148);
+  static const int force_smem = getenv("DFU_CONV_OUT_SMEM") ? atoi(getenv("DFU_CONV_OUT_SMEM")) : -1;  // experiments
+  const long long smem_pix = getenv("DFU_CONV_OUT_SMEM_PIX") ? atoll(getenv("DFU_CONV_OUT_SMEM_PIX")) : 64LL * 8;
+  int w_in_smem = wbytes <= 200 * 1024 && npix >= smem_pix * (num_sms() > 0 ? num_sms() : 148);
+  if (force_smem >= 0 && wbytes <= 200 * 1024) w_in_smem = force_smem;
   if (first_use_on_device(ONCE_CONV_OUT_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_small_out_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_out4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  }
+  DFU_REQUIRE(npix < (1LL << 31), "conv_small_out: %lld pixels exceed the 32-bit index range", npix);
+  static const bool fast4 = !(getenv("DFU_CONV_OUT4") && getenv("DFU_CONV_OUT4")[0] == '0');
+  if (fast4 && ksz == 3 && Cout == 4 && !w2 && W % 4 == 0 && wbytes <= 100 * 1024) {
+    // register-blocked UNet conv_out: one warp per four pixels, at most two CTAs (weights in shared memory) per SM
+    const long long groups = npix / 4;
+    long long nb = (groups + 7) / 8;
+    const long long cap4 = 2LL * (num_sms() > 0 ? num_sms() : 148);
+    if (nb > cap4) nb = cap4;
+    DFU_CHECK_CUDA(launch_k(conv_out4_kernel, dim3(static_cast<unsigned>(nb)), dim3(256), wbytes, static_cast<cudaStream_t>(stream), p));
+    DFU_CHECK_CUDA(cudaGetLastError());
+    return DFU_OK;
   }
   // eight pixels per CTA pass; enough CTAs for every SM, few enough that the weight copy is amortised over many pixels
   const int sms = num_sms() > 0 ? num_sms() : 148;
