@@ -97,8 +97,9 @@ struct SmallInSrc {
   int nhwc;              // 1: sources are NHWC [B,H,W,c] instead of NCHW
 };
 
-constexpr int kSmallInPix = 32;  // output pixels per CTA
+// output pixels per CTA: 32, or 16 when 32 would leave SMs without a second CTA (the 64 x 64 UNet input at batch 1)
 
+template <int kSmallInPix>
 __global__ void __launch_bounds__(512)
 conv_small_in_kernel(SmallInSrc s, int B, int H, int W, int Cin, int ksz, const float* __restrict__ wt,
                      const float* __restrict__ bias, int Cout, float pre_scale, float* __restrict__ out) {
@@ -378,6 +379,7 @@ __global__ void __launch_bounds__(256, kSmemW ? 2 : 4) conv_small_out_kernel(Sma
 // kernel above issues a load per 4-16 FMAs and ran at 8 % of the fp32 peak (125 us at batch 8).  The 16 per-lane partial
 // sums (4 pixels x 4 outputs) are reduced across the warp by halving (16 shuffles instead of 80).
 // ---------------------------------------------------------------------------------------------
+template <int PX>  // pixels of a row per warp
 __global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
   pdl_trigger();
   DFU_TR_BEGIN(TR_CONV_OUT);
@@ -389,27 +391,28 @@ __global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
   pdl_wait();
   DFU_TR_MARK(6);
   const int lane = threadIdx.x & 31;
-  const int W4 = p.W >> 2;
+  const int W4 = p.W / PX;
   const int ngroups = p.B * p.H * W4;
+  constexpr int NP = PX * 4;  // partial sums per lane
   const int nwarps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
   const size_t hw = static_cast<size_t>(p.H) * p.W;
   for (int grp = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5); grp < ngroups; grp += nwarps) {
-    const int x0 = (grp % W4) * 4;
+    const int x0 = (grp % W4) * PX;
     const int yb = grp / W4;
     const int y = yb % p.H;
     const int b = yb / p.H;
-    float acc[16];  // [pixel][output]
+    float acc[NP];  // [pixel][output]
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NP; ++i) acc[i] = 0.f;
     for (int q = lane; q < C4; q += 32) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int iy = y + ky - 1;
         if (iy < 0 || iy >= p.H) continue;  // (warp-uniform)
         const float4* row = reinterpret_cast<const float4*>(p.x + (static_cast<size_t>(b) * p.H + iy) * p.W * p.Cin) + q;
-        float4 in[6];
+        float4 in[PX + 2];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
+        for (int c = 0; c < PX + 2; ++c) {
           const int ix = x0 - 1 + c;
           in[c] = (ix >= 0 && ix < p.W) ? row[static_cast<size_t>(ix) * C4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
           for (int co = 0; co < 4; ++co) {
             const float4 wv = *(reinterpret_cast<const float4*>(sw + (co * 9 + ky * 3 + kx) * p.Cin) + q);
 #pragma unroll
-            for (int px = 0; px < 4; ++px) {
+            for (int px = 0; px < PX; ++px) {
               const float4 v = in[px + kx];
               acc[px * 4 + co] += wv.x * v.x + wv.y * v.y + wv.z * v.z + wv.w * v.w;
             }
@@ -427,11 +430,11 @@ __global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
         }
       }
     }
-    // reduction by halving: after the steps with masks 16, 8, 4, 2 a lane holds ONE of the 16 sums over its half / quarter /
-    // ... of the warp, index ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    // the last step adds the neighbouring lane
+    // reduction by halving: each step with mask m = 16, 8, ... halves the number of sums a lane carries, until it holds
+    // ONE of the NP sums (index = its top log2(NP) lane bits) over part of the warp; the remaining masks are plain adds
+    int m = 16;
 #pragma unroll
-    for (int n = 8, m = 16; n >= 1; n >>= 1, m >>= 1) {
+    for (int n = NP / 2; n >= 1; n >>= 1, m >>= 1) {
       const bool up = (lane & m) != 0;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
@@ -440,9 +443,12 @@ __global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
         acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
       }
     }
-    const float total = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
-    if ((lane & 1) == 0) {
-      const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    float total = acc[0];
+#pragma unroll
+    for (; m >= 1; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+    constexpr int kShift = PX == 4 ? 1 : 2;  // 5 - log2(NP)
+    if ((lane & ((1 << kShift) - 1)) == 0) {
+      const int idx = lane >> kShift;
       const int px = idx >> 2, co = idx & 3;
       const float o = total + (p.bias ? p.bias[co] : 0.f);
       const size_t base = (static_cast<size_t>(b) * 4 + co) * hw + static_cast<size_t>(y) * p.W + x0 + px;
@@ -655,11 +661,15 @@ int dfu_conv_small_in(const float* src0, int c0, int64_t bstride0, const float* 
   s.nhwc = nhwc;
   const long long npix = static_cast<long long>(B) * H * W;
   DFU_REQUIRE(npix < (1LL << 31), "conv_small_in: %lld pixels exceed the 32-bit index range", npix);
-  const int blocks = static_cast<int>((npix + kSmallInPix - 1) / kSmallInPix);
-  const size_t smem = static_cast<size_t>(kSmallInPix) * Cin * ksz * ksz * sizeof(float);
+  static const int pix_env = getenv("DFU_CONV_IN_PIX") ? atoi(getenv("DFU_CONV_IN_PIX")) : 0;
+  const int sms_ = num_sms() > 0 ? num_sms() : 148;
+  const int pix_cta = pix_env ? pix_env : ((npix + 31) / 32 < 2LL * sms_ ? 16 : 32);
+  const int blocks = static_cast<int>((npix + pix_cta - 1) / pix_cta);
+  const size_t smem = static_cast<size_t>(pix_cta) * Cin * ksz * ksz * sizeof(float);
   DFU_REQUIRE(Cout >= 1 && Cout <= 512, "conv_small_in: Cout=%d (one thread per output channel, max 512)", Cout);
   const int threads = ((Cout + 31) / 32) * 32;
-  DFU_CHECK_CUDA(launch_k(conv_small_in_kernel, dim3(blocks), dim3(threads), smem, static_cast<cudaStream_t>(stream), s, B, H, W, Cin, ksz, w, bias, Cout, pre_scale, out));
+  DFU_CHECK_CUDA(launch_k(pix_cta == 16 ? conv_small_in_kernel<16> : conv_small_in_kernel<32>, dim3(blocks), dim3(threads), smem,
+                          static_cast<cudaStream_t>(stream), s, B, H, W, Cin, ksz, w, bias, Cout, pre_scale, out));
   DFU_CHECK_CUDA(cudaGetLastError());
   return DFU_OK;
 }
@@ -686,17 +696,19 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
   if (force_smem >= 0 && wbytes <= 200 * 1024) w_in_smem = force_smem;
   if (first_use_on_device(ONCE_CONV_OUT_ATTR)) {
     DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_small_out_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_out4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_out4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   }
   DFU_REQUIRE(npix < (1LL << 31), "conv_small_out: %lld pixels exceed the 32-bit index range", npix);
   static const bool fast4 = !(getenv("DFU_CONV_OUT4") && getenv("DFU_CONV_OUT4")[0] == '0');
   if (fast4 && ksz == 3 && Cout == 4 && !w2 && W % 4 == 0 && wbytes <= 100 * 1024) {
     // register-blocked UNet conv_out: one warp per four pixels, at most two CTAs (weights in shared memory) per SM
+    // (two pixels per warp for small maps was measured: 12.4 vs 12.6 us at batch 1, slower from batch 2 on)
+    const long long cap4 = 2LL * (num_sms() > 0 ? num_sms() : 148);
     const long long groups = npix / 4;
     long long nb = (groups + 7) / 8;
-    const long long cap4 = 2LL * (num_sms() > 0 ? num_sms() : 148);
     if (nb > cap4) nb = cap4;
-    DFU_CHECK_CUDA(launch_k(conv_out4_kernel, dim3(static_cast<unsigned>(nb)), dim3(256), wbytes, static_cast<cudaStream_t>(stream), p));
+    DFU_CHECK_CUDA(launch_k(conv_out4_kernel<4>, dim3(static_cast<unsigned>(nb)), dim3(256), wbytes,
+                            static_cast<cudaStream_t>(stream), p));
     DFU_CHECK_CUDA(cudaGetLastError());
     return DFU_OK;
   }
