@@ -82,3 +82,25 @@ def test_pipeline_with_native_glyph_encoder():
     err = ((a - b).abs().max() / b.abs().max()).item()
     print(f"pipeline via native glyph encoder vs transformers embeddings: decoded RGB maxrel {err:.3e}")
     assert err < 1e-3
+    # and from the uint8 glyph image itself (what draw_text renders, app.ipynb:347-368): the GPU TrOCRGlyphProcessor +
+    # native encoder against transformers' PIL-backend image processor + ViTModel
+    import numpy as np
+    import transformers
+    from PIL import Image
+    from diffute_b200.glyph_encoder import TrOCRGlyphProcessor
+    if not hasattr(transformers, "ViTImageProcessorPil"):
+        return
+    glyph = np.random.default_rng(2).integers(0, 256, (60, 440, 3), dtype=np.uint8)
+    pipe.glyph_processor = TrOCRGlyphProcessor()
+    a2 = pipe(text=[glyph], **kw).images.cpu()
+    proc = transformers.ViTImageProcessorPil(do_resize=True, size={"height": 384, "width": 384}, resample=2, do_rescale=True,
+                                             rescale_factor=1 / 255, do_normalize=True, image_mean=[0.5] * 3,
+                                             image_std=[0.5] * 3)
+    pv_ref = torch.from_numpy(proc(images=[Image.fromarray(glyph)], return_tensors="np").pixel_values)
+    assert torch.equal(pipe.glyph_processor(images=[glyph]).pixel_values.cpu(), pv_ref)
+    with torch.no_grad():
+        emb = m(pv_ref).last_hidden_state
+    b2 = pipe(glyph_embeds=emb, **kw).images.cpu()
+    err2 = ((a2 - b2).abs().max() / b2.abs().max()).item()
+    print(f"glyph image -> GPU processor -> native encoder -> pipeline vs transformers chain: decoded RGB maxrel {err2:.3e}")
+    assert err2 < 1e-3
