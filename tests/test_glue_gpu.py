@@ -123,3 +123,36 @@ def test_glyph_processor_bit_exact(mods, h, w):
     assert pv.shape == (2, 3, 384, 384) and pv.dtype == torch.float32
     for i, im in enumerate(imgs):
         assert np.array_equal(pv[i].cpu().numpy(), G.vit_pixel_values(im)), (h, w, i)
+
+
+def test_round_trip_properties(mods):
+    """Size-independent properties at a full-size photograph: (1) with a 512-pixel window both resizes are identities, so
+    pre-processing followed by compositing of the untouched crop returns the photograph bit for bit; (2) at other scales
+    the text box is reproduced to within the two bilinear resamplings of a smooth image; (3) the noise stream is a pure
+    function of (seed, step, element): a prefix of a longer draw equals the shorter draw, steps differ."""
+    glue, G = mods
+    from diffute_b200 import ops
+    rng = np.random.default_rng(9)
+    h, w = 2160, 3840
+    image = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    bbox = (1700, 1000, 2100, 1085)                      # 6 * 85 = 510 < 512 -> 512 window: identity resize
+    pre = glue.preprocess(image, bbox)
+    assert pre.window[2] == 512
+    out = glue.composite(pre.image, pre).cpu().numpy()   # "decoded" = the normalised crop itself
+    assert np.array_equal(out, image)
+    yy, xx = np.mgrid[0:h, 0:w]
+    smooth = np.stack([(127 + 100 * np.sin(xx / 97.0) * np.cos(yy / 53.0)), (xx * 255.0 / w), (yy * 255.0 / h)], -1)
+    smooth = np.clip(np.rint(smooth), 0, 255).astype(np.uint8)
+    box2 = (900, 700, 1500, 830)                         # 6 * 130 = 780 < 784 -> 784 window: down to 512 and back up
+    pre2 = glue.preprocess(smooth, box2)
+    assert pre2.window[2] == 784
+    out2 = glue.composite(pre2.image, pre2).cpu().numpy().astype(int)
+    x1, y1, x2, y2 = box2
+    assert np.abs(out2[y1:y2, x1:x2] - smooth[y1:y2, x1:x2].astype(int)).max() <= 2
+    outside = np.ones((h, w), bool)
+    outside[y1:y2, x1:x2] = False
+    assert np.array_equal(out2[outside], smooth[outside].astype(int))
+    a = ops.philox_normal(77, 3, 1 << 20)
+    b = ops.philox_normal(77, 3, 1000)
+    assert torch.equal(a[:1000], b) and not torch.equal(b, ops.philox_normal(77, 4, 1000))
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1.0) < 5e-3

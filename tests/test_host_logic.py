@@ -267,3 +267,28 @@ def test_gemm_plan_tilings_without_gpu():
     assert plan(4096, 320, 320, tune=(48, 1, 3))[0] == -1                  # does not divide n
     assert plan(4096, 2560, 320, epi=2, tune=(80, 1, 3))[0] == -1          # GEGLU pairs value/gate columns in 32s
     assert plan(4096, 320, 320, npass=3, tune=(160, 1, 12))[1][2] < 12    # 12 double-size stages do not fit: clamped
+
+
+def test_crop_window_product_equals_literal_restatement():
+    """diffute_b200.glue.crop_window (table-driven) against the literal restatement of app.ipynb:668-726 in the oracle,
+    including the branches that consult the random generator and the inputs on which the reference raises."""
+    import numpy as np
+    from diffute_b200 import glue as P
+    from oracle import glue as G
+    rng = np.random.default_rng(0)
+    raised = 0
+    for _ in range(4000):
+        h, w = (int(v) for v in rng.integers(64, 2000, 2))
+        x0 = int(rng.integers(0, w - 2)); x1 = int(rng.integers(x0 + 1, w))
+        y0 = int(rng.integers(0, h - 2)); y1 = int(rng.integers(y0 + 1, h))
+        try:
+            ref = G.crop_window((x0, y0, x1, y1), h, w, np.random.RandomState(5))
+        except ValueError:  # np.random.randint(low, high <= low): the reference fails on such boxes
+            raised += 1
+            try:
+                P.crop_window((x0, y0, x1, y1), h, w, np.random.RandomState(5))
+            except ValueError:
+                continue
+            raise AssertionError("product did not raise where the reference does")
+        assert P.crop_window((x0, y0, x1, y1), h, w, np.random.RandomState(5)) == ref, (h, w, x0, y0, x1, y1)
+    assert raised > 0
