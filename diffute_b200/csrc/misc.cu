@@ -379,6 +379,48 @@ __global__ void __launch_bounds__(256, kSmemW ? 2 : 4) conv_small_out_kernel(Sma
 // kernel above issues a load per 4-16 FMAs and ran at 8 % of the fp32 peak (125 us at batch 8).  The 16 per-lane partial
 // sums (4 pixels x 4 outputs) are reduced across the warp by halving (16 shuffles instead of 80).
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// 1x1, few input channels (Cin <= 64): one THREAD per pixel, weights broadcast from shared memory.  The warp-per-pixel
+// kernels above leave 24 of 32 lanes idle at Cin = 32 (the channel-selection conv behind the VAE decoder's tensor-core
+// conv_out, 262 144 pixels: 256 us); here a pixel is 8 x LDG.128 + Cout x 32 FMA in one thread and the NCHW stores of a
+// warp are contiguous.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1x1_pixel_kernel(SmallOut p) {
+  pdl_trigger();
+  DFU_TR_BEGIN(TR_CONV_OUT);
+  __shared__ __align__(16) float sw[8 * 64];
+  __shared__ float sb[8];
+  for (int i = threadIdx.x; i < p.Cout * p.Cin; i += blockDim.x) sw[i] = __ldg(p.w + i);
+  if (threadIdx.x < p.Cout) sb[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
+  __syncthreads();
+  pdl_wait();
+  DFU_TR_MARK(6);
+  const int npix = p.B * p.H * p.W;
+  const int hw = p.H * p.W;
+  const int C4 = p.Cin >> 2;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(pix) * p.Cin);
+    float acc[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) acc[co] = 0.f;
+    for (int q = 0; q < C4; ++q) {
+      const float4 v = xr[q];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) {
+        if (co < p.Cout) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + co * p.Cin + 4 * q);
+          acc[co] += wv.x * v.x + wv.y * v.y + wv.z * v.z + wv.w * v.w;
+        }
+      }
+    }
+    const int b = pix / hw, r = pix - b * hw;
+#pragma unroll
+    for (int co = 0; co < 8; ++co)
+      if (co < p.Cout) p.out[(static_cast<size_t>(b) * p.Cout + co) * hw + r] = acc[co] + sb[co];
+  }
+  DFU_TR_END();
+}
+
 template <int PX>  // pixels of a row per warp
 __global__ void __launch_bounds__(256, 2) conv_out4_kernel(SmallOut p) {
   pdl_trigger();
@@ -699,6 +741,14 @@ int dfu_conv_small_out(const float* x, int B, int H, int W, int Cin, int ksz, co
     DFU_CHECK_CUDA(cudaFuncSetAttribute(conv_out4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   }
   DFU_REQUIRE(npix < (1LL << 31), "conv_small_out: %lld pixels exceed the 32-bit index range", npix);
+  if (ksz == 1 && Cin <= 64 && !w2 && !prev && out && npix >= 65536) {  // large maps only: tiny ones are launch-bound anyway
+    long long nb = (npix + 255) / 256;
+    const long long capp = 8LL * (num_sms() > 0 ? num_sms() : 148);
+    if (nb > capp) nb = capp;
+    DFU_CHECK_CUDA(launch_k(conv1x1_pixel_kernel, dim3(static_cast<unsigned>(nb)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+    DFU_CHECK_CUDA(cudaGetLastError());
+    return DFU_OK;
+  }
   static const bool fast4 = !(getenv("DFU_CONV_OUT4") && getenv("DFU_CONV_OUT4")[0] == '0');
   if (fast4 && ksz == 3 && Cout == 4 && !w2 && W % 4 == 0 && wbytes <= 100 * 1024) {
     // register-blocked UNet conv_out: one warp per four pixels, at most two CTAs (weights in shared memory) per SM

@@ -143,6 +143,19 @@ def test_conv_small_in_out(ops):
     assert _rel(mom, ref) < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 512, 512, 32, 3), (2, 300, 200, 8, 8), (1, 256, 256, 64, 1), (3, 40, 40, 32, 3)])
+def test_conv1x1_few_channels(ops, B, H, W, Cin, Cout):
+    """1x1 conv with few input channels (the selection conv behind the VAE decoder's tensor-core conv_out, the quant
+    convs): large maps take the pixel-per-thread kernel, small ones the warp-per-pixel kernel; same result."""
+    x = _rand((B, H, W, Cin), 31)
+    w = _rand((Cout, Cin, 1, 1), 32, Cin ** -0.5)
+    b = _rand((Cout,), 33)
+    out = torch.full((B, Cout, H, W), float("nan"), device="cuda")
+    ops.conv_small_out(x, ops.pack_small_out_weight(w), b, out)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double())
+    assert _rel(out, ref) < 1e-5
+
+
 def test_elementwise_and_softmax(ops):
     x, e, n = _rand((2, 4, 64, 64), 24), _rand((2, 4, 64, 64), 25), _rand((2, 4, 64, 64), 26)
     y = torch.zeros_like(x)
