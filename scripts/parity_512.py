@@ -1,5 +1,7 @@
 """Full-size parity on the GPU box: 512x512, 50 DDIM steps, decoded RGB vs the fp32 CPU oracle (BASELINE bar 1e-3).
-Writes gpurun_out/parity_512.json.  Usage: python scripts/parity_512.py [px] [steps] [modes...]"""
+Writes gpurun_out/parity_512.json.  Usage: [PARITY_SEED=n] python scripts/parity_512.py [px] [steps] [modes...]
+PARITY_SEED selects other synthetic inputs (latents, image, mask stay a text-line box, glyph embedding) and, with
+PARITY_WSEED, other synthetic weights: the 1e-3 bar is not a property of one draw."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,16 +13,18 @@ px = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 modes = sys.argv[3:] or ["mixed", "fp16x2"]
 torch.set_num_threads(min(os.cpu_count(), int(os.environ.get('DFU_CPU_THREADS', '32'))))
-usd = synthetic.make_state_dict(arch.unet_param_shapes())
-vsd = synthetic.make_state_dict(arch.vae_param_shapes())
-inp = synthetic.make_inputs(1, px, px)
+seed = int(os.environ.get("PARITY_SEED", "0"))
+wseed = int(os.environ.get("PARITY_WSEED", "1234"))
+usd = synthetic.make_state_dict(arch.unet_param_shapes(), wseed)
+vsd = synthetic.make_state_dict(arch.vae_param_shapes(), wseed)
+inp = synthetic.make_inputs(1, px, px, seed=seed)
 uo, vo = UNetOracle(), VAEOracle()
 uo.load_state_dict(usd); vo.load_state_dict(vsd)
 t0 = time.time()
 ref = sample_loop(uo, vo, DDIMOracle(), inp["masked_image"], inp["mask"], inp["glyph_embeds"], inp["latents"], steps,
                   posterior_noise=inp["posterior_noise"])
 t_cpu = time.time() - t0
-res = {"px": px, "steps": steps, "cpu_oracle_seconds": t_cpu, "cpu_threads": torch.get_num_threads(), "modes": {}}
+res = {"px": px, "steps": steps, "input_seed": seed, "weight_seed": wseed, "cpu_oracle_seconds": t_cpu, "cpu_threads": torch.get_num_threads(), "modes": {}}
 for m in modes:
     up, vp = {"mixed": ("fp16", "fp16x2"), "fp16x2": ("fp16x2", "fp16x2"), "fp16": ("fp16", "fp16")}[m]
     pipe = DiffUTEPipeline.from_synthetic(up, vp, state_dicts=(usd, vsd),
@@ -33,5 +37,5 @@ for m in modes:
     del pipe
     torch.cuda.empty_cache()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/parity_512.json", "w"), indent=1)
+json.dump(res, open(f"gpurun_out/parity_512{'' if (seed, wseed) == (0, 1234) else f'_s{seed}_w{wseed}'}.json", "w"), indent=1)
 print(json.dumps(res))
