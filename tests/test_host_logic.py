@@ -292,3 +292,19 @@ def test_crop_window_product_equals_literal_restatement():
             raise AssertionError("product did not raise where the reference does")
         assert P.crop_window((x0, y0, x1, y1), h, w, np.random.RandomState(5)) == ref, (h, w, x0, y0, x1, y1)
     assert raised > 0
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md section 3 names every extern "C" entry point of the header (directly, or through its
+    `name(+_workspace)` / `dfu_trace_set_{a,b}` shorthands)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = sorted(set(re.findall(r"\b(dfu_[a-z0-9_]+)\s*\(", open(os.path.join(root, "include", "diffute_b200.h")).read())))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    expanded = set(re.findall(r"dfu_[a-z0-9_]+", doc))
+    for base, suffix in re.findall(r"(dfu_[a-z0-9_]+)\(\+(_[a-z]+)\)", doc):
+        expanded.add(base + suffix)
+    for prefix, alts in re.findall(r"(dfu_[a-z0-9_]+_)\{([a-z0-9_,]+)\}", doc):
+        expanded.update(prefix + a for a in alts.split(","))
+    missing = [n for n in names if n not in expanded]
+    assert not missing, missing
