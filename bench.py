@@ -340,7 +340,7 @@ def extra_configs(pipe, dev, peaks):
     # ---- the reference's own serving call: text_editing(photo, box) with ITS sampler (ancestral DDPM), uint8 in / out --
     import numpy as np
     from diffute_b200 import glue
-    from diffute_b200.schedulers import DDIMScheduler, DDPMScheduler
+    from diffute_b200.schedulers import DDPMScheduler
     photo = np.random.default_rng(5).integers(0, 256, (1080, 1440, 3), dtype=np.uint8)   # host memory, like cv2.imread
     box = (500, 400, 860, 470)
     emb = dev_inputs(1, PX)["glyph_embeds"]
